@@ -1,0 +1,931 @@
+// Kernels + C ABI of libtriplane_b200.so (see include/triplane_b200.h).  sm_100a only, no CPU path.
+#include "tt_device.cuh"
+#include "../../include/triplane_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+using namespace tt;
+
+// =====================================================================================================
+// host-side helpers
+// =====================================================================================================
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+static int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return TT_E_CUDA;
+    }
+    return TT_OK;
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool supported_C(int C) { return C == 8 || C == 16 || C == 32 || C == 40 || C == 64; }
+
+#define TT_DISPATCH_C(C, ...)                                                    \
+    switch (C) {                                                                 \
+        case 8:  { constexpr int kC = 8;  __VA_ARGS__; } break;                  \
+        case 16: { constexpr int kC = 16; __VA_ARGS__; } break;                  \
+        case 32: { constexpr int kC = 32; __VA_ARGS__; } break;                  \
+        case 40: { constexpr int kC = 40; __VA_ARGS__; } break;                  \
+        case 64: { constexpr int kC = 64; __VA_ARGS__; } break;                  \
+        default: return fail(TT_E_ARG, "unsupported channel count%s %lld (8,16,32,40,64)", "", (long long)(C)); \
+    }
+
+static int check_cfg(const tt_config* cfg) {
+    if (!cfg) return fail(TT_E_ARG, "cfg is NULL%s", "");
+    if (!supported_C(cfg->C)) return fail(TT_E_ARG, "unsupported channel count%s %lld (8,16,32,40,64)", "", cfg->C);
+    if (cfg->R < 2 || cfg->R > 8192) return fail(TT_E_ARG, "plane resolution out of range%s: %lld", "", cfg->R);
+    if (cfg->P < 1) return fail(TT_E_ARG, "P must be >= 1%s (got %lld)", "", cfg->P);
+    if (!(cfg->radius > 0.f)) return fail(TT_E_ARG, "radius must be > 0%s", "");
+    return TT_OK;
+}
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(%zu B smem): %s", bytes, cudaGetErrorString(e)); return TT_E_CUDA; }
+    return TT_OK;
+}
+static inline size_t slab_bytes(int rows) { return (size_t)rows * ST * sizeof(float); }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+// =====================================================================================================
+// weights
+// =====================================================================================================
+__global__ void k_pack_weights(const float* s0, const float* s1, const float* s2, const float* f0, const float* f1,
+                               const float* f2, const float* d0, const float* d1, const float* d2, int C, float* wp) {
+    const WOff wo = woff(C);
+    const int n = blockDim.x * gridDim.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    auto both = [&](const float* src, int rows, int cols, int dst, int dstT) {   // src [rows][cols]
+        if (!src) return;
+        for (int i = t; i < rows * cols; i += n) {
+            const int r = i / cols, c = i % cols;
+            const float v = src[i];
+            wp[dst + i] = v;
+            wp[dstT + c * rows + r] = v;
+        }
+    };
+    auto plain = [&](const float* src, int cnt, int dst) {
+        if (!src) return;
+        for (int i = t; i < cnt; i += n) wp[dst + i] = src[i];
+    };
+    both(s0, 64, C, wo.w1s, wo.w1sT); both(s1, 64, 64, wo.w2s, wo.w2sT); plain(s2, 64, wo.w3s);
+    both(f0, 64, 3 * C, wo.w1f, wo.w1fT); both(f1, 64, 64, wo.w2f, wo.w2fT); plain(f2, 192, wo.w3f);
+    both(d0, 64, C, wo.w1d, wo.w1dT); both(d1, 64, 64, wo.w2d, wo.w2dT); plain(d2, 192, wo.w3d);
+}
+
+// =====================================================================================================
+// plane repack: NCHW (un-rotated) <-> channel-last (rotated)
+// rotated[h][w] = src[sh][sw]:  plane%3==0: transpose (sh=w, sw=h); ==1: rot90 k=2 (sh=R-1-h, sw=R-1-w);
+// ==2: rot90 k=-1 (sh=R-1-w, sw=h)            (few_step…diffusion.py:212-225)
+// =====================================================================================================
+__device__ __forceinline__ void rot_dst(int k3, int R, int sh, int sw, int& h, int& w) {
+    if (k3 == 0) { h = sw; w = sh; }
+    else if (k3 == 1) { h = R - 1 - sh; w = R - 1 - sw; }
+    else { h = sw; w = R - 1 - sh; }
+}
+// grid: (ceil(R/32), R, P*6); block (32, 8).  Tile = one source row segment of 32 texels, all channels.
+template <bool BWD>
+__global__ void k_repack(const float* __restrict__ src, float* __restrict__ dst, int Csrc, int off_geo, int off_tex,
+                         int C, int R) {
+    TT_SHARED(tile);                         // [C][33]
+    const int pk = blockIdx.z, k = pk % 6, sh = blockIdx.y, sw0 = blockIdx.x * 32;
+    const int coff = (k < 3) ? off_geo : off_tex;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const size_t nchw_plane = (size_t)pk * Csrc * R * R;
+    const size_t cl_plane = (size_t)pk * R * R * C;
+    if (!BWD) {
+        for (int c = ty; c < C; c += 8)
+            if (sw0 + tx < R) tile[c * 33 + tx] = src[nchw_plane + ((size_t)(coff + c) * R + sh) * R + sw0 + tx];
+        __syncthreads();
+        for (int i = ty; i < 32 && sw0 + i < R; i += 8) {
+            int h, w; rot_dst(k % 3, R, sh, sw0 + i, h, w);
+            for (int c = tx; c < C; c += 32) dst[cl_plane + ((size_t)h * R + w) * C + c] = tile[c * 33 + i];
+        }
+    } else {   // src = channel-last gradient, dst = NCHW gradient (Csrc == C, offsets 0)
+        for (int i = ty; i < 32 && sw0 + i < R; i += 8) {
+            int h, w; rot_dst(k % 3, R, sh, sw0 + i, h, w);
+            for (int c = tx; c < C; c += 32) tile[c * 33 + i] = src[cl_plane + ((size_t)h * R + w) * C + c];
+        }
+        __syncthreads();
+        for (int c = ty; c < C; c += 8)
+            if (sw0 + tx < R) dst[nchw_plane + ((size_t)c * R + sh) * R + sw0 + tx] = tile[c * 33 + tx];
+    }
+}
+
+// =====================================================================================================
+// point sources
+// =====================================================================================================
+struct RaySrc {
+    const float* rays_o; const float* rays_d;
+    const float* t_starts; const float* t_ends; int64_t t_stride; int S;
+};
+// isosurface grid vertex (threestudio/models/isosurface.py:37-51): linspace(0,1,res) -> scale to (-1,1)
+__device__ __forceinline__ float grid_coord(int i, int res) {
+    // torch.linspace(0, 1, res): step = 1/(res-1); first half start + i*step, second half end - (res-1-i)*step
+    const float step = __fdiv_rn(1.f, (float)(res - 1));
+    float v = (i < res / 2) ? __fmul_rn((float)i, step) : __fsub_rn(1.f, __fmul_rn((float)(res - 1 - i), step));
+    v = __fadd_rn(__fmul_rn(v, 1.f), 0.f);
+    return __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(v, 0.f), 1.f), 2.f), -1.f);
+}
+
+// =====================================================================================================
+// geometry on point lists (forward / forward_sdf / forward_field / export)
+// =====================================================================================================
+template <int C>
+__global__ void __launch_bounds__(TPB) k_geometry_fwd(const float* __restrict__ planes, const float* __restrict__ wp,
+                                                     tt_config cfg, const float* __restrict__ points, int64_t M,
+                                                     int grid_res, float* sdf_o, float* sdf_orig_o, float* feat_o,
+                                                     float* normal_o, float* grad_o, float* deform_o) {
+    TT_SHARED(smem);
+    constexpr int RX = C > HID ? C : HID;
+    float* slotX = smem + threadIdx.x;
+    float* slotB = smem + RX * ST + threadIdx.x;
+    const WOff wo = woff(C);
+    const int64_t N = (int64_t)cfg.P * M;
+    const int64_t idx = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (idx >= N) return;
+    const int prompt = (int)(idx / M);
+    float x[3];
+    if (points) { x[0] = points[idx * 3]; x[1] = points[idx * 3 + 1]; x[2] = points[idx * 3 + 2]; }
+    else {
+        const int64_t v = idx % M;
+        const int iz = (int)(v % grid_res), iy = (int)((v / grid_res) % grid_res), ixx = (int)(v / ((int64_t)grid_res * grid_res));
+        x[0] = grid_coord(ixx, grid_res); x[1] = grid_coord(iy, grid_res); x[2] = grid_coord(iz, grid_res);
+    }
+    const size_t ps = (size_t)cfg.R * cfg.R * C;
+    const float* geo = planes + (size_t)prompt * 6 * ps;
+    const bool want_n = normal_o || grad_o;
+    float so, s, g[3] = {0.f, 0.f, 0.f};
+    if (want_n) geo_eval<C, true>(geo, cfg.R, wp, wo, x, cfg.radius, cfg.sdf_bias_radius, slotX, slotB, so, s, g);
+    else geo_eval<C, false>(geo, cfg.R, wp, wo, x, cfg.radius, cfg.sdf_bias_radius, slotX, slotB, so, s, g);
+    if (sdf_o) sdf_o[idx] = s;
+    if (sdf_orig_o) sdf_orig_o[idx] = so;
+    if (grad_o) { grad_o[idx * 3] = g[0]; grad_o[idx * 3 + 1] = g[1]; grad_o[idx * 3 + 2] = g[2]; }
+    if (normal_o) {
+        float n[3], len; normalize3(g, n, len);
+        normal_o[idx * 3] = n[0]; normal_o[idx * 3 + 1] = n[1]; normal_o[idx * 3 + 2] = n[2];
+    }
+    if (deform_o) {   // deformation MLP on the same geometry encoding (few_step…diffusion.py:375-394); slotX still holds it
+        float acc[HID];
+        zero64(acc); layer64_acc(acc, wp + wo.w1dT, C, slotX); store_relu64(acc, slotB);
+        zero64(acc); layer64_acc(acc, wp + wo.w2dT, HID, slotB);
+        float d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
+            const float h = fmaxf(acc[j], 0.f);
+            d[0] = fmaf(h, __ldg(wp + wo.w3d + j), d[0]);
+            d[1] = fmaf(h, __ldg(wp + wo.w3d + HID + j), d[1]);
+            d[2] = fmaf(h, __ldg(wp + wo.w3d + 2 * HID + j), d[2]);
+        }
+        deform_o[idx * 3] = d[0]; deform_o[idx * 3 + 1] = d[1]; deform_o[idx * 3 + 2] = d[2];
+    }
+    if (feat_o) {
+        float p[3], f[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
+        tex_eval<C>(geo + 3 * ps, cfg.R, wp, wo, p, slotX, slotB, f);
+        feat_o[idx * 3] = f[0]; feat_o[idx * 3 + 1] = f[1]; feat_o[idx * 3 + 2] = f[2];
+    }
+}
+
+// =====================================================================================================
+// importance sampling (one thread per ray)
+// =====================================================================================================
+__device__ __forceinline__ float quantile(int j, int n, bool strat, float b) {
+    return strat ? __fdiv_rn(__fadd_rn((float)j, b), (float)(n + 1)) : __fdiv_rn((float)j, (float)n);
+}
+__device__ __forceinline__ float stot(float s, float tmin, float tmax) {    // estimators.py:104-118 (uniform)
+    return __fadd_rn(__fmul_rn(s, tmax), __fmul_rn(__fsub_rn(1.f, s), tmin));
+}
+template <int C>
+__global__ void __launch_bounds__(TPB) k_importance_sample(const float* __restrict__ planes, const float* __restrict__ wp,
+                                                          tt_config cfg, const float* __restrict__ rays_o,
+                                                          const float* __restrict__ rays_d, int64_t n_rays, int n_imp,
+                                                          int n_fine, const float* __restrict__ jit0,
+                                                          const float* __restrict__ jit1, float* __restrict__ cdf,
+                                                          float* __restrict__ t_vals) {
+    TT_SHARED(smem);
+    constexpr int RX = C > HID ? C : HID;
+    float* slotX = smem + threadIdx.x;
+    float* slotB = smem + RX * ST + threadIdx.x;
+    const WOff wo = woff(C);
+    const int64_t ray = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (ray >= n_rays) return;
+    const int prompt = (int)(ray / cfg.rays_per_cache);
+    const size_t ps = (size_t)cfg.R * cfg.R * C;
+    const float* geo = planes + (size_t)prompt * 6 * ps;
+    const float o[3] = {rays_o[ray * 3], rays_o[ray * 3 + 1], rays_o[ray * 3 + 2]};
+    const float d[3] = {rays_d[ray * 3], rays_d[ray * 3 + 1], rays_d[ray * 3 + 2]};
+    const bool strat = jit0 != nullptr;
+    const float b0 = strat ? jit0[ray] : 0.f, b1 = strat ? jit1[ray] : 0.f;
+    const float step = cfg.render_step_size;
+    // level 0: the [0,1] cdf maps quantile u to s = u (nerfacc importance_sampling on the unit interval)
+    float run = 0.f;                              // exclusive sum of sigma*dt
+    float s_lo = quantile(0, n_imp, strat, b0);
+    float t_lo = stot(s_lo, cfg.near_plane, cfg.far_plane);
+    for (int j = 0; j < n_imp; ++j) {
+        const float s_hi = quantile(j + 1, n_imp, strat, b0);
+        const float t_hi = stot(s_hi, cfg.near_plane, cfg.far_plane);
+        cdf[(size_t)j * n_rays + ray] = 1.f - expf(-run);
+        const float tm = __fmul_rn(__fadd_rn(t_lo, t_hi), 0.5f);
+        const float x[3] = {__fadd_rn(o[0], __fmul_rn(d[0], tm)), __fadd_rn(o[1], __fmul_rn(d[1], tm)),
+                            __fadd_rn(o[2], __fmul_rn(d[2], tm))};
+        float so, s, g[3];
+        geo_eval<C, false>(geo, cfg.R, wp, wo, x, cfg.radius, cfg.sdf_bias_radius, slotX, slotB, so, s, g);
+        // proposal density (…sdf_volume_renderer.py:289-297)
+        const float pc = sigmoidf((s + step * 0.5f) * cfg.inv_std), nc = sigmoidf((s - step * 0.5f) * cfg.inv_std);
+        const float alpha = fminf(fmaxf((pc - nc + 1e-5f) / (pc + 1e-5f), 0.f), 1.f);
+        const float sigma = alpha / step;
+        run += sigma * (t_hi - t_lo);
+        t_lo = t_hi;
+    }
+    cdf[(size_t)n_imp * n_rays + ray] = 1.f;
+    // fine edges by inverse CDF + merge with the coarse edges into one sorted row
+    const int n_in = n_imp + 1, n_out = n_imp + n_fine + 2;
+    float* out = t_vals + (size_t)ray * n_out;
+    int k = 0; float last = -3.0e38f;
+    auto emit = [&](float v) {
+        if (v >= last) { out[k] = v; last = v; }
+        else { int j = k; while (j > 0 && out[j - 1] > v) { out[j] = out[j - 1]; --j; } out[j] = v; }
+        ++k;
+    };
+    int a = 0;                                    // next coarse edge to emit
+    float ta = stot(quantile(0, n_imp, strat, b0), cfg.near_plane, cfg.far_plane);
+    int p = 0;                                    // searchsorted pointer (count of cdf <= u)
+    for (int j = 0; j <= n_fine; ++j) {
+        const float u = quantile(j, n_fine, strat, b1);
+        while (p < n_in && cdf[(size_t)p * n_rays + ray] <= u) ++p;
+        const int pc = min(max(p, 1), n_in - 1);
+        const float c0 = cdf[(size_t)(pc - 1) * n_rays + ray], c1 = cdf[(size_t)pc * n_rays + ray];
+        const float v0 = quantile(pc - 1, n_imp, strat, b0), v1 = quantile(pc, n_imp, strat, b0);
+        const float den = __fsub_rn(c1, c0);
+        float fr = den > 0.f ? __fdiv_rn(__fsub_rn(u, c0), den) : 0.f;
+        fr = fminf(fmaxf(fr, 0.f), 1.f);
+        const float sv = __fadd_rn(v0, __fmul_rn(fr, __fsub_rn(v1, v0)));
+        const float tf = stot(sv, cfg.near_plane, cfg.far_plane);
+        while (a < n_in && ta <= tf) {
+            emit(ta); ++a;
+            if (a < n_in) ta = stot(quantile(a, n_imp, strat, b0), cfg.near_plane, cfg.far_plane);
+        }
+        emit(tf);
+    }
+    while (a < n_in) {
+        emit(ta); ++a;
+        if (a < n_in) ta = stot(quantile(a, n_imp, strat, b0), cfg.near_plane, cfg.far_plane);
+    }
+}
+
+// =====================================================================================================
+// fused march + decoders + alpha + compositing (one thread per ray, lock-step over the S intervals)
+// =====================================================================================================
+template <int C>
+__global__ void __launch_bounds__(TPB) k_render_fwd(const float* __restrict__ planes, const float* __restrict__ wp,
+                                                   tt_config cfg, RaySrc rs, int64_t n_rays, float* __restrict__ acc_o,
+                                                   float* sdf_o, float* sdf_orig_o, float* grad_o, float* normal_o,
+                                                   float* feat_o, float* weights_o, float* trans_o) {
+    TT_SHARED(smem);
+    constexpr int RX = C > HID ? C : HID;
+    float* slotX = smem + threadIdx.x;
+    float* slotB = smem + RX * ST + threadIdx.x;
+    const WOff wo = woff(C);
+    const int64_t ray = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (ray >= n_rays) return;
+    const int prompt = (int)(ray / cfg.rays_per_cache);
+    const size_t ps = (size_t)cfg.R * cfg.R * C;
+    const float* geo = planes + (size_t)prompt * 6 * ps;
+    const float o[3] = {rs.rays_o[ray * 3], rs.rays_o[ray * 3 + 1], rs.rays_o[ray * 3 + 2]};
+    const float d[3] = {rs.rays_d[ray * 3], rs.rays_d[ray * 3 + 1], rs.rays_d[ray * 3 + 2]};
+    const float* t0p = rs.t_starts + ray * rs.t_stride;
+    const float* t1p = rs.t_ends + ray * rs.t_stride;
+    const int S = rs.S;
+    float T = 1.f, opac = 0.f, depth = 0.f, rgb[3] = {0.f, 0.f, 0.f}, nsum[3] = {0.f, 0.f, 0.f};
+    float wsum = 0.f, mean = 0.f, m2 = 0.f;      // weighted Welford for z_variance
+    for (int i = 0; i < S; ++i) {
+        const float t0 = t0p[i], t1 = t1p[i];
+        const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f), dt = __fsub_rn(t1, t0);
+        const float x[3] = {__fadd_rn(o[0], __fmul_rn(d[0], tm)), __fadd_rn(o[1], __fmul_rn(d[1], tm)),
+                            __fadd_rn(o[2], __fmul_rn(d[2], tm))};
+        float so, s, g[3];
+        geo_eval<C, true>(geo, cfg.R, wp, wo, x, cfg.radius, cfg.sdf_bias_radius, slotX, slotB, so, s, g);
+        float n[3], len; normalize3(g, n, len);
+        const AlphaTerms at = neus_alpha(s, n, d, dt, cfg.inv_std, cfg.cos_anneal_ratio);
+        float p[3], f[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
+        tex_eval<C>(geo + 3 * ps, cfg.R, wp, wo, p, slotX, slotB, f);
+        const float w = T * at.alpha;
+        opac += w; depth = fmaf(w, tm, depth);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { rgb[a] = fmaf(w, sigmoid_mipnerf(f[a]), rgb[a]); nsum[a] = fmaf(w, n[a], nsum[a]); }
+        const float wn = wsum + w;
+        if (wn > 0.f) { const float dl = tm - mean; mean += (w / wn) * dl; m2 += w * dl * (tm - mean); }
+        wsum = wn;
+        const int64_t si = ray * S + i;
+        if (sdf_o) sdf_o[si] = s;
+        if (sdf_orig_o) sdf_orig_o[si] = so;
+        if (grad_o) { grad_o[si * 3] = g[0]; grad_o[si * 3 + 1] = g[1]; grad_o[si * 3 + 2] = g[2]; }
+        if (normal_o) { normal_o[si * 3] = n[0]; normal_o[si * 3 + 1] = n[1]; normal_o[si * 3 + 2] = n[2]; }
+        if (feat_o) { feat_o[si * 3] = f[0]; feat_o[si * 3 + 1] = f[1]; feat_o[si * 3 + 2] = f[2]; }
+        if (weights_o) weights_o[si] = w;
+        if (trans_o) trans_o[si] = T;
+        T *= (1.f - at.alpha);
+    }
+    float* a = acc_o + ray * 9;
+    a[0] = opac; a[1] = depth; a[2] = rgb[0]; a[3] = rgb[1]; a[4] = rgb[2];
+    a[5] = m2 + wsum * (mean - depth) * (mean - depth);      // Σ w (t - depth)^2, depth un-normalised
+    a[6] = nsum[0]; a[7] = nsum[1]; a[8] = nsum[2];
+}
+
+// =====================================================================================================
+// backward, stage 1: compositing + alpha + normalisation, one thread per ray, reverse order.
+// Writes per-sample seeds for stage 2: gs (d/d sdf), u[3] (d/d sdf_grad), gf[3] (d/d features).
+// =====================================================================================================
+__global__ void __launch_bounds__(TPB) k_render_bwd_comp(tt_config cfg, RaySrc rs, int64_t n_rays,
+        const float* __restrict__ acc, const float* __restrict__ sdf, const float* __restrict__ grad,
+        const float* __restrict__ feat, const float* __restrict__ trans, const float* __restrict__ g_acc,
+        const float* __restrict__ g_sdf, const float* __restrict__ g_grad, const float* __restrict__ g_normal,
+        const float* __restrict__ g_feat, const float* __restrict__ g_weights, float rgb_scale,
+        float* __restrict__ gs_o, float* __restrict__ u_o, float* __restrict__ gf_o, float* g_inv_std) {
+    const int64_t ray = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    float gis = 0.f;
+    if (ray < n_rays) {
+        const float d[3] = {rs.rays_d[ray * 3], rs.rays_d[ray * 3 + 1], rs.rays_d[ray * 3 + 2]};
+        const float* t0p = rs.t_starts + ray * rs.t_stride;
+        const float* t1p = rs.t_ends + ray * rs.t_stride;
+        const int S = rs.S;
+        const float* ga = g_acc + ray * 9;
+        const float opac = acc[ray * 9], D = acc[ray * 9 + 1];
+        const float gO = ga[0], gZ = ga[5];
+        const float gD = ga[1] + gZ * (-2.f) * D * (1.f - opac);    // z_variance depends on depth[ray]
+        const float gC[3] = {ga[2], ga[3], ga[4]}, gN[3] = {ga[6], ga[7], ga[8]};
+        const float car = cfg.cos_anneal_ratio, inv_std = cfg.inv_std;
+        float Rh = 0.f;     // Σ_{j>i} gw_j α_j Π_{i<k<j} (1-α_k)
+        for (int i = S - 1; i >= 0; --i) {
+            const int64_t si = ray * S + i;
+            const float t0 = t0p[i], t1 = t1p[i];
+            const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f), dt = __fsub_rn(t1, t0);
+            const float s = sdf[si];
+            const float g[3] = {grad[si * 3], grad[si * 3 + 1], grad[si * 3 + 2]};
+            const float f[3] = {feat[si * 3], feat[si * 3 + 1], feat[si * 3 + 2]};
+            const float T = trans[si];
+            float n[3], len; normalize3(g, n, len);
+            const AlphaTerms at = neus_alpha(s, n, d, dt, inv_std, car);
+            const float w = T * at.alpha;
+            float c[3], sg[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { sg[a] = sigmoidf(f[a]); c[a] = sg[a] * 1.002f - 0.001f; }
+            float gw = gO + gD * tm + gC[0] * c[0] + gC[1] * c[1] + gC[2] * c[2] + gN[0] * n[0] + gN[1] * n[1] +
+                       gN[2] * n[2] + gZ * (tm - D) * (tm - D);
+            if (g_weights) gw += g_weights[si];
+            const float galpha = T * (gw - Rh);
+            Rh = gw * at.alpha + (1.f - at.alpha) * Rh;
+            // colour
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float v = w * gC[a] * rgb_scale * 1.002f * sg[a] * (1.f - sg[a]);
+                if (g_feat) v += g_feat[si * 3 + a];
+                gf_o[si * 3 + a] = v;
+            }
+            // alpha -> sdf, normal
+            float gn[3] = {w * gN[0], w * gN[1], w * gN[2]};
+            if (g_normal) { gn[0] += g_normal[si * 3]; gn[1] += g_normal[si * 3 + 1]; gn[2] += g_normal[si * 3 + 2]; }
+            float gsdf = g_sdf ? g_sdf[si] : 0.f;
+            if (at.alpha_raw >= 0.f && at.alpha_raw <= 1.f && galpha != 0.f) {
+                const float den = at.prev_cdf + 1e-5f;
+                const float gnum = galpha / den, gden = -galpha * at.alpha_raw / den;
+                const float gpc = gnum + gden, gnc = -gnum;
+                const float dp = at.prev_cdf * (1.f - at.prev_cdf), dn = at.next_cdf * (1.f - at.next_cdf);
+                const float gsp = gpc * dp * inv_std, gsn = gnc * dn * inv_std;
+                gis += gpc * dp * at.s_prev + gnc * dn * at.s_next;
+                gsdf += gsp + gsn;
+                const float giter = (gsn - gsp) * dt * 0.5f;
+                const float dct = 0.5f * (1.f - car) * ((-at.true_cos * 0.5f + 0.5f) > 0.f ? 1.f : 0.f) +
+                                  car * ((-at.true_cos) > 0.f ? 1.f : 0.f);
+                const float gtc = giter * dct;
+                gn[0] += gtc * d[0]; gn[1] += gtc * d[1]; gn[2] += gtc * d[2];
+            }
+            // n = g / max(|g|, eps)
+            float u[3] = {0.f, 0.f, 0.f};
+            if (len > 1e-12f) {
+                const float dotv = n[0] * gn[0] + n[1] * gn[1] + n[2] * gn[2];
+                const float il = 1.f / len;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) u[a] = (gn[a] - n[a] * dotv) * il;
+            } else {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) u[a] = gn[a] * 1e12f;
+            }
+            if (g_grad) { u[0] += g_grad[si * 3]; u[1] += g_grad[si * 3 + 1]; u[2] += g_grad[si * 3 + 2]; }
+            gs_o[si] = gsdf;
+            u_o[si * 3] = u[0]; u_o[si * 3 + 1] = u[1]; u_o[si * 3 + 2] = u[2];
+        }
+    }
+    if (g_inv_std) {
+#ifndef TT_EMUL
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) gis += __shfl_xor_sync(0xffffffffu, gis, off);
+        if ((threadIdx.x & 31) == 0 && gis != 0.f) atomicAdd(g_inv_std, gis);
+#else
+        if (gis != 0.f) atomicAdd(g_inv_std, gis);
+#endif
+    }
+}
+
+// seeds for the stand-alone geometry backward: gs = g_sdf, u = g_sdf_grad + d normalize, gf = g_features
+__global__ void k_geometry_bwd_seed(int64_t N, const float* __restrict__ grad /*sdf_grad, needed iff g_normal*/,
+                                    const float* g_sdf, const float* g_feat, const float* g_normal,
+                                    const float* g_grad, float* gs_o, float* u_o, float* gf_o) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    gs_o[i] = g_sdf ? g_sdf[i] : 0.f;
+    float u[3] = {0.f, 0.f, 0.f};
+    if (g_normal) {
+        const float g[3] = {grad[i * 3], grad[i * 3 + 1], grad[i * 3 + 2]};
+        const float gn[3] = {g_normal[i * 3], g_normal[i * 3 + 1], g_normal[i * 3 + 2]};
+        float n[3], len; normalize3(g, n, len);
+        if (len > 1e-12f) {
+            const float dotv = n[0] * gn[0] + n[1] * gn[1] + n[2] * gn[2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) u[a] = (gn[a] - n[a] * dotv) / len;
+        } else {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) u[a] = gn[a] * 1e12f;
+        }
+    }
+    if (g_grad) { u[0] += g_grad[i * 3]; u[1] += g_grad[i * 3 + 1]; u[2] += g_grad[i * 3 + 2]; }
+    u_o[i * 3] = u[0]; u_o[i * 3 + 1] = u[1]; u_o[i * 3 + 2] = u[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) gf_o[i * 3 + a] = g_feat ? g_feat[i * 3 + a] : 0.f;
+}
+
+// =====================================================================================================
+// backward, stage 2a: SDF decoder + geometry planes, one thread per sample point.
+//   L depends on sdf (seed gs) and on sdf_grad = d sdf/d x (seed u).  With the tap weights
+//   ω = gs·w + ẇ (ẇ = directional derivative of the bilinear weights along u) and ẽ = Σ ω·texel:
+//     dL/dW1 = a1 ẽᵀ, dL/dW2 = a2 h̃1ᵀ, dL/dw3 = h̃2,  h̃1 = m1⊙W1ẽ, h̃2 = m2⊙W2h̃1,
+//     dL/dtexel = (W1ᵀa1)·ω          (a1, a2: unit-seed adjoints of the SDF MLP)
+//   which is the function of grid_sample_gradfix/gridsample_cuda.cu:87-209 fused with the MLP terms.
+// =====================================================================================================
+struct PtSrc {
+    const float* points; int64_t M;     // explicit points [P*M][3] (prompt = idx / M) or NULL
+    RaySrc rs; int rays_per_cache;      // else sample idx = ray*S + i
+};
+__device__ __forceinline__ void point_of(const PtSrc& src, int64_t idx, float (&x)[3], int& prompt) {
+    if (src.points) {
+        x[0] = src.points[idx * 3]; x[1] = src.points[idx * 3 + 1]; x[2] = src.points[idx * 3 + 2];
+        prompt = (int)(idx / src.M);
+    } else {
+        const int64_t ray = idx / src.rs.S; const int i = (int)(idx % src.rs.S);
+        const float t0 = src.rs.t_starts[ray * src.rs.t_stride + i], t1 = src.rs.t_ends[ray * src.rs.t_stride + i];
+        const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(src.rs.rays_o[ray * 3 + a], __fmul_rn(src.rs.rays_d[ray * 3 + a], tm));
+        prompt = (int)(ray / src.rays_per_cache);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(TPB) k_bwd_geo(const float* __restrict__ planes, const float* __restrict__ wp,
+                                                tt_config cfg, PtSrc src, int64_t N, const float* __restrict__ gs_i,
+                                                const float* __restrict__ u_i, float* __restrict__ gplanes,
+                                                float* __restrict__ gw) {
+    TT_SHARED(smem);
+    constexpr int RE = C;
+    float* sE = smem;                       // C rows:  enc -> ẽ
+    float* sB = sE + RE * ST;               // 64 rows: h1 -> a2 -> a1 -> a2 -> h̃2
+    float* sD = sB + HID * ST;              // C rows:  W1ᵀ a1
+    float* sT = sD + C * ST;                // 64 rows: h̃1
+    const int tid = threadIdx.x;
+    const WOff wo = woff(C);
+    const GOff go = goff(C);
+    const int64_t idx = (int64_t)blockIdx.x * TPB + tid;
+    float gs = 0.f, u[3] = {0.f, 0.f, 0.f};
+    bool active = idx < N;
+    if (active) {
+        gs = gs_i[idx]; u[0] = u_i[idx * 3]; u[1] = u_i[idx * 3 + 1]; u[2] = u_i[idx * 3 + 2];
+        active = (gs != 0.f) || (u[0] != 0.f) || (u[1] != 0.f) || (u[2] != 0.f);
+    }
+    if (!__syncthreads_or(active)) return;
+    PointTaps pt; float om[12]; uint64_t m1 = 0, m2 = 0;
+    const size_t ps = (size_t)cfg.R * cfg.R * C;
+    const float* geo = planes; float* ggeo = gplanes;
+    if (active) {
+        float x[3]; int prompt;
+        point_of(src, idx, x, prompt);
+        geo = planes + (size_t)prompt * 6 * ps; ggeo = gplanes + (size_t)prompt * 6 * ps;
+        float p[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
+        Taps tp[3];
+        point_taps(p, cfg.R, pt, tp);
+        const float sc = 0.5f * (float)cfg.R / cfg.radius;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float ixd = u[plane_ax(k)] * sc, iyd = u[plane_ay(k)] * sc;
+            om[k * 4 + 0] = gs * tp[k].w[0] + (-tp[k].wy0 * ixd - tp[k].wx0 * iyd);
+            om[k * 4 + 1] = gs * tp[k].w[1] + (tp[k].wy0 * ixd - tp[k].wx1 * iyd);
+            om[k * 4 + 2] = gs * tp[k].w[2] + (-tp[k].wy1 * ixd + tp[k].wx0 * iyd);
+            om[k * 4 + 3] = gs * tp[k].w[3] + (tp[k].wy1 * ixd + tp[k].wx1 * iyd);
+        }
+        gather<C, 3>(geo, ps, pt.o, pt.w, sE + tid);
+        float acc[HID];
+        zero64(acc); layer64_acc(acc, wp + wo.w1sT, C, sE + tid); m1 = store_relu64(acc, sB + tid);
+        zero64(acc); layer64_acc(acc, wp + wo.w2sT, HID, sB + tid); m2 = mask64(acc);
+#pragma unroll
+        for (int j = 0; j < HID; ++j) sB[j * ST + tid] = ((m2 >> j) & 1ull) ? __ldg(wp + wo.w3s + j) : 0.f;
+        zero64(acc); layerT_acc<HID>(acc, wp + wo.w2s, HID, sB + tid); store_masked64(acc, m1, sB + tid);   // a1
+        float de[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) de[c] = 0.f;
+        layerT_acc<C>(de, wp + wo.w1s, C, sB + tid);
+#pragma unroll
+        for (int c = 0; c < C; ++c) sD[c * ST + tid] = de[c];
+        gather<C, 3>(geo, ps, pt.o, om, sE + tid);            // ẽ
+    } else {
+        zero_col(sE + tid, RE); zero_col(sB + tid, HID); zero_col(sT + tid, HID);
+    }
+    __syncthreads();
+    if (gw) wgrad(gw + go.g1s, C, sB, HID, sE, C);            // dW1 += a1 ẽᵀ
+    if (active) {
+        float acc[HID];
+        zero64(acc); layer64_acc(acc, wp + wo.w1sT, C, sE + tid); store_masked64(acc, m1, sT + tid);   // h̃1
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < HID; ++j) sB[j * ST + tid] = ((m2 >> j) & 1ull) ? __ldg(wp + wo.w3s + j) : 0.f;   // a2
+    }
+    __syncthreads();
+    if (gw) wgrad(gw + go.g2s, HID, sB, HID, sT, HID);        // dW2 += a2 h̃1ᵀ
+    {
+        float acc[HID];
+        zero64(acc);
+        if (active) layer64_acc(acc, wp + wo.w2sT, HID, sT + tid);
+        __syncthreads();
+        store_masked64(acc, m2, sB + tid);                     // h̃2 (zero for inactive threads: m2 = 0)
+    }
+    __syncthreads();
+    if (gw && tid < HID) {                                     // dw3 += Σ_p h̃2
+        float s = 0.f;
+        for (int p = 0; p < TPB; ++p) s += sB[tid * ST + p];
+        if (s != 0.f) atomicAdd(gw + go.g3s + tid, s);
+    }
+    if (active && gplanes) scatter_col<C, 3>(ggeo, ps, pt.o, om, sD + tid);
+}
+
+// =====================================================================================================
+// backward, stage 2b: colour decoder + texture planes, one thread per sample point (seed gf[3])
+// =====================================================================================================
+template <int C>
+__global__ void __launch_bounds__(TPB) k_bwd_tex(const float* __restrict__ planes, const float* __restrict__ wp,
+                                                tt_config cfg, PtSrc src, int64_t N, const float* __restrict__ gf_i,
+                                                float* __restrict__ gplanes, float* __restrict__ gw) {
+    TT_SHARED(smem);
+    float* sX = smem;                       // C rows: one texture plane's encoding
+    float* sA = sX + C * ST;                // 64 rows: h1
+    float* sB = sA + HID * ST;              // 64 rows: h2 -> g_h2 -> g_h1
+    float* sG = sB + HID * ST;              // 4 rows: gf
+    const int tid = threadIdx.x;
+    const WOff wo = woff(C);
+    const GOff go = goff(C);
+    const int64_t idx = (int64_t)blockIdx.x * TPB + tid;
+    float gf[3] = {0.f, 0.f, 0.f};
+    bool active = idx < N;
+    if (active) {
+        gf[0] = gf_i[idx * 3]; gf[1] = gf_i[idx * 3 + 1]; gf[2] = gf_i[idx * 3 + 2];
+        active = (gf[0] != 0.f) || (gf[1] != 0.f) || (gf[2] != 0.f);
+    }
+    if (!__syncthreads_or(active)) return;
+    const size_t ps = (size_t)cfg.R * cfg.R * C;
+    const float* tex = planes; float* gtex = gplanes;
+    float p[3] = {0.f, 0.f, 0.f};
+    uint64_t m1 = 0, m2 = 0;
+    if (active) {
+        float x[3]; int prompt;
+        point_of(src, idx, x, prompt);
+        tex = planes + ((size_t)prompt * 6 + 3) * ps; gtex = gplanes + ((size_t)prompt * 6 + 3) * ps;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
+        float acc[HID];
+        zero64(acc);
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+            const Taps t = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
+            gather<C, 1>(tex + k * ps, 0, t.o, t.w, sX + tid);
+            layer64_acc(acc, wp + wo.w1fT + k * C * HID, C, sX + tid);
+        }
+        m1 = store_relu64(acc, sA + tid);
+        zero64(acc); layer64_acc(acc, wp + wo.w2fT, HID, sA + tid); m2 = store_relu64(acc, sB + tid);
+    } else {
+        zero_col(sA + tid, HID); zero_col(sB + tid, HID); zero_col(sX + tid, C);
+    }
+    sG[tid] = gf[0]; sG[ST + tid] = gf[1]; sG[2 * ST + tid] = gf[2]; sG[3 * ST + tid] = 0.f;
+    __syncthreads();
+    if (gw) wgrad(gw + go.g3f, HID, sG, 3, sB, HID);          // dW3 += gf h2ᵀ
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
+            const float v = gf[0] * __ldg(wp + wo.w3f + j) + gf[1] * __ldg(wp + wo.w3f + HID + j) +
+                            gf[2] * __ldg(wp + wo.w3f + 2 * HID + j);
+            sB[j * ST + tid] = ((m2 >> j) & 1ull) ? v : 0.f;  // g_h2
+        }
+    }
+    __syncthreads();
+    if (gw) wgrad(gw + go.g2f, HID, sB, HID, sA, HID);        // dW2 += g_h2 h1ᵀ
+    __syncthreads();
+    if (active) {
+        float acc[HID];
+        zero64(acc); layerT_acc<HID>(acc, wp + wo.w2f, HID, sB + tid); store_masked64(acc, m1, sB + tid);   // g_h1
+    }
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        Taps t;
+        if (active) {
+            t = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
+            gather<C, 1>(tex + k * ps, 0, t.o, t.w, sX + tid);
+        }
+        __syncthreads();
+        if (gw) wgrad(gw + go.g1f + k * C, 3 * C, sB, HID, sX, C);   // dW1[:, kC:(k+1)C] += g_h1 enc_kᵀ
+        __syncthreads();
+        if (active && gplanes) {
+            float ge[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) ge[c] = 0.f;
+            layerT_acc<C>(ge, wp + wo.w1f + k * C, 3 * C, sB + tid);
+#pragma unroll
+            for (int c = 0; c < C; ++c) sX[c * ST + tid] = ge[c];
+            scatter_col<C, 1>(gtex + k * ps, 0, t.o, t.w, sX + tid);
+        }
+    }
+}
+
+// =====================================================================================================
+// stand-alone compositor (nerfacc.render_weight_from_alpha + accumulate_along_rays, dense rays)
+// =====================================================================================================
+__global__ void k_composite_fwd(const float* __restrict__ alphas, const float* __restrict__ values, int64_t n_rays,
+                                int S, int D, float* weights, float* trans, float* out) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    float T = 1.f, acc[8];
+    const int Do = D > 0 ? D : 1;
+    for (int k = 0; k < Do; ++k) acc[k] = 0.f;
+    for (int i = 0; i < S; ++i) {
+        const int64_t si = ray * S + i;
+        const float a = alphas[si], w = T * a;
+        if (weights) weights[si] = w;
+        if (trans) trans[si] = T;
+        if (D > 0) { for (int k = 0; k < D; ++k) acc[k] = fmaf(w, values[si * D + k], acc[k]); }
+        else acc[0] += w;
+        T *= (1.f - a);
+    }
+    if (out) for (int k = 0; k < Do; ++k) out[ray * Do + k] = acc[k];
+}
+__global__ void k_composite_bwd(const float* __restrict__ alphas, const float* __restrict__ values,
+                                const float* __restrict__ trans, const float* __restrict__ g_out,
+                                const float* __restrict__ g_weights, int64_t n_rays, int S, int D, float* g_alphas,
+                                float* g_values) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    const int Do = D > 0 ? D : 1;
+    float go[8];
+    for (int k = 0; k < Do; ++k) go[k] = g_out ? g_out[ray * Do + k] : 0.f;
+    float Rh = 0.f;
+    for (int i = S - 1; i >= 0; --i) {
+        const int64_t si = ray * S + i;
+        const float a = alphas[si], T = trans[si], w = T * a;
+        float gw = g_weights ? g_weights[si] : 0.f;
+        if (D > 0) {
+            for (int k = 0; k < D; ++k) {
+                gw = fmaf(go[k], values[si * D + k], gw);
+                if (g_values) g_values[si * D + k] = w * go[k];
+            }
+        } else gw += go[0];
+        g_alphas[si] = T * (gw - Rh);
+        Rh = gw * a + (1.f - a) * Rh;
+    }
+}
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int tt_version(void) { return TT_VERSION; }
+const char* tt_last_error(void) { return g_err; }
+int64_t tt_launch_count(void) { return g_launches.load(); }
+int tt_device_ok(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) { cudaGetLastError(); return 0; }
+    return 1;
+}
+size_t tt_wpack_floats(int C) { return supported_C(C) ? (size_t)woff(C).total : 0; }
+size_t tt_wgrad_floats(int C) { return supported_C(C) ? (size_t)goff(C).total : 0; }
+int tt_wgrad_offsets(int C, int64_t off[6]) {
+    if (!supported_C(C) || !off) return fail(TT_E_ARG, "tt_wgrad_offsets: bad arguments%s", "");
+    const GOff g = goff(C);
+    off[0] = g.g1s; off[1] = g.g2s; off[2] = g.g3s; off[3] = g.g1f; off[4] = g.g2f; off[5] = g.g3f;
+    return TT_OK;
+}
+
+int tt_pack_weights(const float* s0, const float* s1, const float* s2, const float* f0, const float* f1,
+                    const float* f2, const float* d0, const float* d1, const float* d2, int C, float* wpack,
+                    void* stream) {
+    if (!supported_C(C)) return fail(TT_E_ARG, "unsupported channel count%s %lld (8,16,32,40,64)", "", C);
+    if (!s0 || !s1 || !s2 || !wpack) return fail(TT_E_ARG, "tt_pack_weights: sdf weights and wpack are required%s", "");
+    if ((f0 || f1 || f2) && !(f0 && f1 && f2)) return fail(TT_E_ARG, "tt_pack_weights: feature weights must be all set or all NULL%s", "");
+    if ((d0 || d1 || d2) && !(d0 && d1 && d2)) return fail(TT_E_ARG, "tt_pack_weights: deformation weights must be all set or all NULL%s", "");
+    if (!aligned16(wpack)) return fail(TT_E_ALIGN, "wpack must be 16-byte aligned%s", "");
+    TT_LAUNCH(k_pack_weights, 32, 256, 0, (cudaStream_t)stream, s0, s1, s2, f0, f1, f2, d0, d1, d2, C, wpack);
+    return check_launch("tt_pack_weights");
+}
+
+int tt_repack_planes(const float* src, int P, int Csrc, int off_geo, int off_tex, int C, int R, float* dst, void* stream) {
+    if (!src || !dst) return fail(TT_E_ARG, "tt_repack_planes: NULL pointer%s", "");
+    if (P < 1 || R < 1 || C < 1 || off_geo < 0 || off_tex < 0 || off_geo + C > Csrc || off_tex + C > Csrc)
+        return fail(TT_E_ARG, "tt_repack_planes: bad shape%s", "");
+    if (C > 256) return fail(TT_E_ARG, "tt_repack_planes: C too large%s (%lld)", "", C);
+    dim3 grid((R + 31) / 32, R, P * 6), block(32, 8);
+    TT_LAUNCH(k_repack<false>, grid, block, (size_t)C * 33 * 4, (cudaStream_t)stream, src, dst, Csrc, off_geo, off_tex, C, R);
+    return check_launch("tt_repack_planes");
+}
+int tt_repack_planes_bwd(const float* gplanes, int P, int C, int R, float* gsrc, void* stream) {
+    if (!gplanes || !gsrc) return fail(TT_E_ARG, "tt_repack_planes_bwd: NULL pointer%s", "");
+    if (P < 1 || R < 1 || C < 1 || C > 256) return fail(TT_E_ARG, "tt_repack_planes_bwd: bad shape%s", "");
+    dim3 grid((R + 31) / 32, R, P * 6), block(32, 8);
+    TT_LAUNCH(k_repack<true>, grid, block, (size_t)C * 33 * 4, (cudaStream_t)stream, gplanes, gsrc, C, 0, 0, C, R);
+    return check_launch("tt_repack_planes_bwd");
+}
+
+int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cfg, const float* points, int64_t M,
+                    int grid_res, float* sdf, float* sdf_orig, float* features, float* normal, float* sdf_grad,
+                    float* deformation, void* stream) {
+    if (int e = check_cfg(cfg)) return e;
+    if (!planes || !wpack) return fail(TT_E_ARG, "tt_geometry_fwd: planes/wpack NULL%s", "");
+    if (!points) {
+        if (grid_res < 2) return fail(TT_E_ARG, "tt_geometry_fwd: points NULL needs grid_res >= 2%s", "");
+        M = (int64_t)grid_res * grid_res * grid_res;
+    }
+    if (M < 0) return fail(TT_E_ARG, "tt_geometry_fwd: M < 0%s", "");
+    if (!aligned16(planes) || !aligned16(wpack)) return fail(TT_E_ALIGN, "planes/wpack must be 16-byte aligned%s", "");
+    const int64_t N = (int64_t)cfg->P * M;
+    if (N == 0) return TT_OK;
+    const int64_t blocks = (N + TPB - 1) / TPB;
+    if (blocks > 2147483647LL) return fail(TT_E_ARG, "tt_geometry_fwd: too many points%s (%lld)", "", N);
+    TT_DISPATCH_C(cfg->C, {
+        const size_t sm = slab_bytes(imax(kC, HID) + HID);
+        if (int e = set_smem(k_geometry_fwd<kC>, sm)) return e;
+        TT_LAUNCH(k_geometry_fwd<kC>, (unsigned)blocks, TPB, sm, (cudaStream_t)stream, planes, wpack, *cfg, points, M, grid_res,
+            sdf, sdf_orig, features, normal, sdf_grad, deformation);
+    });
+    return check_launch("tt_geometry_fwd");
+}
+
+size_t tt_sample_scratch_floats(int64_t n_rays, int n_imp) { return (size_t)n_rays * (size_t)(n_imp + 1); }
+
+int tt_importance_sample(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
+                         const float* rays_d, int64_t n_rays, int n_imp, int n_fine, const float* jitter0,
+                         const float* jitter1, float* scratch, float* t_vals, void* stream) {
+    if (int e = check_cfg(cfg)) return e;
+    if (!planes || !wpack || !rays_o || !rays_d || !scratch || !t_vals) return fail(TT_E_ARG, "tt_importance_sample: NULL pointer%s", "");
+    if (n_imp < 1 || n_fine < 1) return fail(TT_E_ARG, "tt_importance_sample: n_imp and n_fine must be >= 1%s", "");
+    if ((jitter0 == nullptr) != (jitter1 == nullptr)) return fail(TT_E_ARG, "tt_importance_sample: both jitters or none%s", "");
+    if (cfg->rays_per_cache < 1 || n_rays > (int64_t)cfg->P * cfg->rays_per_cache)
+        return fail(TT_E_ARG, "tt_importance_sample: n_rays exceeds P*rays_per_cache%s (%lld)", "", n_rays);
+    if (!aligned16(planes) || !aligned16(wpack)) return fail(TT_E_ALIGN, "planes/wpack must be 16-byte aligned%s", "");
+    if (n_rays <= 0) return TT_OK;
+    const int64_t blocks = (n_rays + TPB - 1) / TPB;
+    TT_DISPATCH_C(cfg->C, {
+        const size_t sm = slab_bytes(imax(kC, HID) + HID);
+        if (int e = set_smem(k_importance_sample<kC>, sm)) return e;
+        TT_LAUNCH(k_importance_sample<kC>, (unsigned)blocks, TPB, sm, (cudaStream_t)stream, planes, wpack, *cfg, rays_o, rays_d,
+            n_rays, n_imp, n_fine, jitter0, jitter1, scratch, t_vals);
+    });
+    return check_launch("tt_importance_sample");
+}
+
+static int check_rays(const char* who, const tt_config* cfg, const float* rays_o, const float* rays_d, int64_t n_rays,
+                      const float* t0, const float* t1, int64_t t_stride, int S) {
+    if (!rays_o || !rays_d || !t0 || !t1) return fail(TT_E_ARG, "%s: NULL ray/interval pointer", who);
+    if (S < 1 || t_stride < S) return fail(TT_E_ARG, "%s: bad S / t_stride", who);
+    if (cfg->rays_per_cache < 1 || n_rays > (int64_t)cfg->P * cfg->rays_per_cache)
+        return fail(TT_E_ARG, "%s: n_rays exceeds P*rays_per_cache (%lld)", who, n_rays);
+    return TT_OK;
+}
+
+int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
+                  const float* rays_d, int64_t n_rays, const float* t_starts, const float* t_ends, int64_t t_stride,
+                  int S, float* acc, float* sdf, float* sdf_orig, float* sdf_grad, float* normal, float* features,
+                  float* weights, float* trans, void* stream) {
+    if (int e = check_cfg(cfg)) return e;
+    if (!planes || !wpack || !acc) return fail(TT_E_ARG, "tt_render_fwd: NULL pointer%s", "");
+    if (int e = check_rays("tt_render_fwd", cfg, rays_o, rays_d, n_rays, t_starts, t_ends, t_stride, S)) return e;
+    if (!aligned16(planes) || !aligned16(wpack)) return fail(TT_E_ALIGN, "planes/wpack must be 16-byte aligned%s", "");
+    if (n_rays <= 0) return TT_OK;
+    const RaySrc rs{rays_o, rays_d, t_starts, t_ends, t_stride, S};
+    const int64_t blocks = (n_rays + TPB - 1) / TPB;
+    TT_DISPATCH_C(cfg->C, {
+        const size_t sm = slab_bytes(imax(kC, HID) + HID);
+        if (int e = set_smem(k_render_fwd<kC>, sm)) return e;
+        TT_LAUNCH(k_render_fwd<kC>, (unsigned)blocks, TPB, sm, (cudaStream_t)stream, planes, wpack, *cfg, rs, n_rays, acc, sdf,
+            sdf_orig, sdf_grad, normal, features, weights, trans);
+    });
+    return check_launch("tt_render_fwd");
+}
+
+static int launch_point_bwd(const float* planes, const float* wpack, const tt_config* cfg, const PtSrc& src, int64_t N,
+                            const float* gs, const float* u, const float* gf, float* gplanes, float* gw,
+                            cudaStream_t st) {
+    const int64_t blocks = (N + TPB - 1) / TPB;
+    if (blocks > 2147483647LL) return fail(TT_E_ARG, "too many sample points%s (%lld)", "", N);
+    TT_DISPATCH_C(cfg->C, {
+        const size_t smg = slab_bytes(kC + HID + kC + HID);
+        if (int e = set_smem(k_bwd_geo<kC>, smg)) return e;
+        TT_LAUNCH(k_bwd_geo<kC>, (unsigned)blocks, TPB, smg, st, planes, wpack, *cfg, src, N, gs, u, gplanes, gw);
+        if (int e = check_launch("k_bwd_geo")) return e;
+        const size_t smt = slab_bytes(kC + HID + HID + 4);
+        if (int e = set_smem(k_bwd_tex<kC>, smt)) return e;
+        TT_LAUNCH(k_bwd_tex<kC>, (unsigned)blocks, TPB, smt, st, planes, wpack, *cfg, src, N, gf, gplanes, gw);
+        if (int e = check_launch("k_bwd_tex")) return e;
+    });
+    return TT_OK;
+}
+
+size_t tt_render_bwd_scratch_floats(int64_t n_rays, int S) { return (size_t)n_rays * (size_t)S * 7; }
+
+int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
+                  const float* rays_d, int64_t n_rays, const float* t_starts, const float* t_ends, int64_t t_stride,
+                  int S, const float* acc, const float* sdf, const float* sdf_grad, const float* features,
+                  const float* trans, const float* g_acc, const float* g_sdf, const float* g_sdf_grad,
+                  const float* g_normal, const float* g_features, const float* g_weights, float rgb_grad_scale,
+                  float* scratch, float* gplanes, float* gw, float* g_inv_std, void* stream) {
+    if (int e = check_cfg(cfg)) return e;
+    if (!planes || !wpack || !acc || !sdf || !sdf_grad || !features || !trans || !g_acc || !scratch)
+        return fail(TT_E_ARG, "tt_render_bwd: NULL pointer%s", "");
+    if (int e = check_rays("tt_render_bwd", cfg, rays_o, rays_d, n_rays, t_starts, t_ends, t_stride, S)) return e;
+    if (!aligned16(planes) || !aligned16(wpack) || (gplanes && !aligned16(gplanes)))
+        return fail(TT_E_ALIGN, "planes/wpack/gplanes must be 16-byte aligned%s", "");
+    if (n_rays <= 0) return TT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const RaySrc rs{rays_o, rays_d, t_starts, t_ends, t_stride, S};
+    const int64_t N = n_rays * S;
+    float* gs = scratch; float* u = scratch + N; float* gf = scratch + 4 * N;
+    TT_LAUNCH(k_render_bwd_comp, (unsigned)((n_rays + TPB - 1) / TPB), TPB, 0, st, *cfg, rs, n_rays, acc, sdf, sdf_grad, features,
+        trans, g_acc, g_sdf, g_sdf_grad, g_normal, g_features, g_weights, rgb_grad_scale, gs, u, gf, g_inv_std);
+    if (int e = check_launch("k_render_bwd_comp")) return e;
+    if (!gplanes && !gw) return TT_OK;
+    PtSrc src; src.points = nullptr; src.M = 0; src.rs = rs; src.rays_per_cache = cfg->rays_per_cache;
+    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, gplanes, gw, st);
+}
+
+size_t tt_geometry_bwd_scratch_floats(int64_t n_points) { return (size_t)n_points * 10; }
+
+int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* points, int64_t M,
+                       const float* g_sdf, const float* g_features, const float* g_normal, const float* g_sdf_grad,
+                       float* scratch, float* gplanes, float* gw, void* stream) {
+    if (int e = check_cfg(cfg)) return e;
+    if (!planes || !wpack || !points || !scratch) return fail(TT_E_ARG, "tt_geometry_bwd: NULL pointer%s", "");
+    if (!aligned16(planes) || !aligned16(wpack) || (gplanes && !aligned16(gplanes)))
+        return fail(TT_E_ALIGN, "planes/wpack/gplanes must be 16-byte aligned%s", "");
+    const int64_t N = (int64_t)cfg->P * M;
+    if (N <= 0) return TT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* gs = scratch; float* u = scratch + N; float* gf = scratch + 4 * N; float* grad = scratch + 7 * N;
+    if (g_normal) {   // the normalisation Jacobian needs sdf_grad: recompute it
+        if (int e = tt_geometry_fwd(planes, wpack, cfg, points, M, 0, nullptr, nullptr, nullptr, nullptr, grad, nullptr, stream)) return e;
+    }
+    TT_LAUNCH(k_geometry_bwd_seed, (unsigned)((N + 255) / 256), 256, 0, st, N, grad, g_sdf, g_features, g_normal, g_sdf_grad, gs, u, gf);
+    if (int e = check_launch("k_geometry_bwd_seed")) return e;
+    PtSrc src; src.points = points; src.M = M; src.rs = RaySrc{nullptr, nullptr, nullptr, nullptr, 0, 1}; src.rays_per_cache = 1;
+    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, gplanes, gw, st);
+}
+
+int tt_composite_fwd(const float* alphas, const float* values, int64_t n_rays, int S, int D, float* weights,
+                     float* trans, float* out, void* stream) {
+    if (!alphas || S < 1 || D < 0 || D > 8 || (D > 0 && !values)) return fail(TT_E_ARG, "tt_composite_fwd: bad arguments%s", "");
+    if (n_rays <= 0) return TT_OK;
+    TT_LAUNCH(k_composite_fwd, (unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream, alphas, values, n_rays, S, D, weights, trans, out);
+    return check_launch("tt_composite_fwd");
+}
+int tt_composite_bwd(const float* alphas, const float* values, const float* trans, const float* g_out,
+                     const float* g_weights, int64_t n_rays, int S, int D, float* g_alphas, float* g_values,
+                     void* stream) {
+    if (!alphas || !trans || !g_alphas || S < 1 || D < 0 || D > 8 || (D > 0 && !values))
+        return fail(TT_E_ARG, "tt_composite_bwd: bad arguments%s", "");
+    if (n_rays <= 0) return TT_OK;
+    TT_LAUNCH(k_composite_bwd, (unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream, alphas, values, trans, g_out, g_weights,
+        n_rays, S, D, g_alphas, g_values);
+    return check_launch("tt_composite_bwd");
+}
+
+}  // extern "C"
