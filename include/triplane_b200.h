@@ -41,6 +41,7 @@ extern "C" {
 #endif
 
 #define TT_VERSION 100
+#define TT_ACC 10 /* per-ray accumulators written by tt_render_fwd */
 
 enum {
     TT_OK = 0,
@@ -135,7 +136,10 @@ int tt_importance_sample(const float* planes, const float* wpack, const tt_confi
  * normals, NoMaterial, NeuSVolumeRenderer.get_alpha (neus_volume_renderer.py:93-117),
  * nerfacc.render_weight_from_alpha and the five nerfacc.accumulate_along_rays calls.
  * t_starts/t_ends: rows of S floats, consecutive rows t_stride floats apart.
- * acc out: [n_rays][9] = opacity, depth, rgb[3], z_variance, normal_sum[3] (un-normalised).
+ * acc out: [n_rays][TT_ACC] = opacity, depth, rgb[3], z_variance, normal_sum[3] (un-normalised),
+ * eikonal_sum = Σ_samples (|sdf_grad| - 1)^2 (the eikonal loss of
+ * custom/triplaneturbo/systems/multiprompt_dual_renderer_multistep_generator.py:690-714 without materialising
+ * sdf_grad).
  * Per-sample outputs [n_rays*S] (all nullable; needed by tt_render_bwd: sdf, sdf_grad,
  * features, trans): sdf, sdf_orig, sdf_grad[3], normal[3], features[3], weights, trans. */
 int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
@@ -144,7 +148,7 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
                   float* acc,
                   float* sdf, float* sdf_orig, float* sdf_grad, float* normal, float* features,
                   float* weights, float* trans, void* stream);
-/* Backward.  g_acc: [n_rays][9] gradients of the accumulators.  Per-sample upstream
+/* Backward.  g_acc: [n_rays][TT_ACC] gradients of the accumulators.  Per-sample upstream
  * gradients (nullable): g_sdf [N], g_sdf_grad [N][3], g_normal [N][3], g_features [N][3],
  * g_weights [N].  rgb_grad_scale multiplies the colour gradient (rgb_grad_shrink,
  * …sdf_volume_renderer.py:397-400).  scratch: tt_render_bwd_scratch_floats() floats.
@@ -173,6 +177,10 @@ int tt_composite_bwd(const float* alphas, const float* values, const float* tran
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t tt_launch_count(void);
+/* Per-launch device timing for bench.py's roofline: between begin and end every kernel launch is bracketed by
+ * CUDA events on its stream; end synchronises and writes "kernel:milliseconds;" records into buf. */
+int tt_profile_begin(void);
+int tt_profile_end(char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

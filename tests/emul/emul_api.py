@@ -129,7 +129,7 @@ class Emul:
         t0, t1 = f32(t_starts), f32(t_ends)
         n, S = t0.shape
         N = n * S
-        out = dict(acc=np.zeros((n, 9), np.float32), sdf=np.zeros(N, np.float32), sdf_orig=np.zeros(N, np.float32),
+        out = dict(acc=np.zeros((n, 10), np.float32), sdf=np.zeros(N, np.float32), sdf_orig=np.zeros(N, np.float32),
                    sdf_grad=np.zeros((N, 3), np.float32), normal=np.zeros((N, 3), np.float32),
                    features=np.zeros((N, 3), np.float32), weights=np.zeros(N, np.float32),
                    trans=np.zeros(N, np.float32))

@@ -31,6 +31,8 @@ SIGNATURES = {
     "tt_last_error": (C.c_char_p, []),
     "tt_device_ok": (C.c_int, []),
     "tt_launch_count": (i64, []),
+    "tt_profile_begin": (C.c_int, []),
+    "tt_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
     "tt_wpack_floats": (C.c_size_t, [C.c_int]),
     "tt_wgrad_floats": (C.c_size_t, [C.c_int]),
     "tt_wgrad_offsets": (C.c_int, [C.c_int, C.POINTER(i64)]),

@@ -17,7 +17,14 @@
 #pragma once
 #ifndef TT_EMUL   // TT_EMUL: host emulation used only by tests/emul (see tests/emul/cuda_emul.h)
 #include <cuda_runtime.h>
-#define TT_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+void tt_prof_pre(cudaStream_t st);
+void tt_prof_post(const char* name, cudaStream_t st);
+#define TT_LAUNCH(kernel, grid, block, smem, stream, ...)                \
+    do {                                                                 \
+        tt_prof_pre(stream);                                             \
+        kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);              \
+        tt_prof_post(#kernel, stream);                                   \
+    } while (0)
 #define TT_SHARED(name) extern __shared__ __align__(16) float name[]
 #endif
 #include <stdint.h>

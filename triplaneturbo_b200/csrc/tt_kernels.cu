@@ -27,6 +27,28 @@ static int check_launch(const char* what) {
     }
     return TT_OK;
 }
+// ---- optional per-launch timing (CUDA events on the launching stream), off by default ------------------
+#ifndef TT_EMUL
+#include <string>
+#include <vector>
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static cudaEvent_t g_prof_pending = nullptr;
+void tt_prof_pre(cudaStream_t st) {
+    if (!g_prof_on) return;
+    cudaEventCreate(&g_prof_pending);
+    cudaEventRecord(g_prof_pending, st);
+}
+void tt_prof_post(const char* name, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r; r.name = name; r.a = g_prof_pending;
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.b, st);
+    g_prof.push_back(r);
+}
+#endif
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static bool supported_C(int C) { return C == 8 || C == 16 || C == 32 || C == 40 || C == 64; }
 
@@ -310,6 +332,7 @@ __global__ void __launch_bounds__(TPB) k_render_fwd(const float* __restrict__ pl
     const int S = rs.S;
     float T = 1.f, opac = 0.f, depth = 0.f, rgb[3] = {0.f, 0.f, 0.f}, nsum[3] = {0.f, 0.f, 0.f};
     float wsum = 0.f, mean = 0.f, m2 = 0.f;      // weighted Welford for z_variance
+    float eik = 0.f;                             // Σ (|sdf_grad| - 1)^2 (eikonal term, un-weighted)
     for (int i = 0; i < S; ++i) {
         const float t0 = t0p[i], t1 = t1p[i];
         const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f), dt = __fsub_rn(t1, t0);
@@ -319,6 +342,7 @@ __global__ void __launch_bounds__(TPB) k_render_fwd(const float* __restrict__ pl
         geo_eval<C, true>(geo, cfg.R, wp, wo, x, cfg.radius, cfg.sdf_bias_radius, slotX, slotB, so, s, g);
         float n[3], len; normalize3(g, n, len);
         const AlphaTerms at = neus_alpha(s, n, d, dt, cfg.inv_std, cfg.cos_anneal_ratio);
+        eik += (len - 1.f) * (len - 1.f);
         float p[3], f[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
@@ -340,10 +364,11 @@ __global__ void __launch_bounds__(TPB) k_render_fwd(const float* __restrict__ pl
         if (trans_o) trans_o[si] = T;
         T *= (1.f - at.alpha);
     }
-    float* a = acc_o + ray * 9;
+    float* a = acc_o + ray * TT_ACC;
     a[0] = opac; a[1] = depth; a[2] = rgb[0]; a[3] = rgb[1]; a[4] = rgb[2];
     a[5] = m2 + wsum * (mean - depth) * (mean - depth);      // Σ w (t - depth)^2, depth un-normalised
     a[6] = nsum[0]; a[7] = nsum[1]; a[8] = nsum[2];
+    a[9] = eik;
 }
 
 // =====================================================================================================
@@ -363,8 +388,9 @@ __global__ void __launch_bounds__(TPB) k_render_bwd_comp(tt_config cfg, RaySrc r
         const float* t0p = rs.t_starts + ray * rs.t_stride;
         const float* t1p = rs.t_ends + ray * rs.t_stride;
         const int S = rs.S;
-        const float* ga = g_acc + ray * 9;
-        const float opac = acc[ray * 9], D = acc[ray * 9 + 1];
+        const float* ga = g_acc + ray * TT_ACC;
+        const float opac = acc[ray * TT_ACC], D = acc[ray * TT_ACC + 1];
+        const float gE = ga[9];
         const float gO = ga[0], gZ = ga[5];
         const float gD = ga[1] + gZ * (-2.f) * D * (1.f - opac);    // z_variance depends on depth[ray]
         const float gC[3] = {ga[2], ga[3], ga[4]}, gN[3] = {ga[6], ga[7], ga[8]};
@@ -426,6 +452,10 @@ __global__ void __launch_bounds__(TPB) k_render_bwd_comp(tt_config cfg, RaySrc r
                 for (int a = 0; a < 3; ++a) u[a] = gn[a] * 1e12f;
             }
             if (g_grad) { u[0] += g_grad[si * 3]; u[1] += g_grad[si * 3 + 1]; u[2] += g_grad[si * 3 + 2]; }
+            if (gE != 0.f && len > 0.f) {                       // d (|g|-1)^2 / d g = 2 (|g|-1) g / |g|
+                const float ce = gE * 2.f * (len - 1.f) / len;
+                u[0] += ce * g[0]; u[1] += ce * g[1]; u[2] += ce * g[2];
+            }
             gs_o[si] = gsdf;
             u_o[si * 3] = u[0]; u_o[si * 3 + 1] = u[1]; u_o[si * 3 + 2] = u[2];
         }
@@ -724,6 +754,33 @@ extern "C" {
 int tt_version(void) { return TT_VERSION; }
 const char* tt_last_error(void) { return g_err; }
 int64_t tt_launch_count(void) { return g_launches.load(); }
+int tt_profile_begin(void) {
+#ifndef TT_EMUL
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = true;
+#endif
+    return TT_OK;
+}
+int tt_profile_end(char* buf, size_t cap) {
+    if (buf && cap) buf[0] = 0;
+#ifndef TT_EMUL
+    g_prof_on = false;
+    size_t used = 0;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.b);
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        if (buf) {
+            const int n = snprintf(buf + used, used < cap ? cap - used : 0, "%s:%.6f;", r.name.c_str(), ms);
+            if (n > 0 && used + (size_t)n < cap) used += (size_t)n;
+        }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+#endif
+    return TT_OK;
+}
 int tt_device_ok(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) { cudaGetLastError(); return 0; }

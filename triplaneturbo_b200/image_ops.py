@@ -14,7 +14,9 @@ from torch import Tensor
 def compose_images(acc: Tensor, bg_color: Tensor, camera_distances: Optional[Tensor], c2w: Optional[Tensor],
                    B: int, H: int, W: int, normal_direction: str = "camera", views_per_cache: int = 1
                    ) -> Dict[str, Tensor]:
-    """acc [Nr,9] = opacity, depth, rgb(3), z_variance, normal_sum(3)  ->  the renderer's image dictionary."""
+    """acc [Nr,10] = opacity, depth, rgb(3), z_variance, normal_sum(3), eikonal_sum -> the renderer's image
+    dictionary (plus ``eikonal_sum`` [B,H,W,1]: Σ_samples (|sdf_grad|-1)^2 per ray, an extension that lets the
+    eikonal loss be taken without per-sample tensors)."""
     opacity, depth = acc[:, 0:1], acc[:, 1:2]
     comp_rgb_fg, z_variance, nsum = acc[:, 2:5], acc[:, 5:6], acc[:, 6:9]
     comp_rgb_bg = bg_color
@@ -28,6 +30,7 @@ def compose_images(acc: Tensor, bg_color: Tensor, camera_distances: Optional[Ten
         "opacity": opacity.reshape(B, H, W, 1),
         "depth": depth.reshape(B, H, W, 1),
         "z_variance": z_variance.reshape(B, H, W, 1),
+        "eikonal_sum": acc[:, 9:10].reshape(B, H, W, 1),
     }
     if camera_distances is not None:                                       # :451-462, RichDreamer disparity
         sqrt3 = torch.sqrt(3 * torch.ones(1, 1, 1, 1, device=acc.device, dtype=acc.dtype))
