@@ -63,12 +63,19 @@ typedef struct {
     float cos_anneal_ratio;  /* threestudio/models/renderers/neus_volume_renderer.py:91 */
     float near_plane, far_plane; /* yaml :145-146 */
     float render_step_size;  /* neus_volume_renderer.py:84-86 */
+    int32_t flags;           /* TT_FLAG_* */
 } tt_config;
+#define TT_FLAG_ALL_FEATURES 1 /* tt_render_fwd: evaluate the colour decoder at every sample, not only where the
+                                  transmittance is > 0 (needed when `features` is returned to the caller) */
 
 int tt_version(void);
 const char* tt_last_error(void);
 /* 1 if a CUDA device is usable by this library, else 0 (never falls back to the CPU). */
 int tt_device_ok(void);
+/* Kernel family: 1 (default) = tcgen05 tensor-core kernels (3xTF32, TMEM accumulators), 0 = SIMT fp32 reference
+ * kernels.  Both are CUDA; parity tests run both. */
+int tt_set_impl(int impl);
+int tt_get_impl(void);
 
 /* ---- decoder weights -----------------------------------------------------------------
  * Replaces: the nn.Linear parameters of VanillaMLP (threestudio/models/networks.py:67-104)
@@ -141,13 +148,15 @@ int tt_importance_sample(const float* planes, const float* wpack, const tt_confi
  * custom/triplaneturbo/systems/multiprompt_dual_renderer_multistep_generator.py:690-714 without materialising
  * sdf_grad).
  * Per-sample outputs [n_rays*S] (all nullable; needed by tt_render_bwd: sdf, sdf_grad,
- * features, trans): sdf, sdf_orig, sdf_grad[3], normal[3], features[3], weights, trans. */
+ * features, trans): sdf, sdf_orig, sdf_grad[3], normal[3], features[3], weights, trans.
+ * scratch: tt_render_fwd_scratch_floats() floats (holds the per-sample state the caller did not ask for). */
+size_t tt_render_fwd_scratch_floats(int64_t n_rays, int S);
 int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
                   const float* rays_o, const float* rays_d, int64_t n_rays,
                   const float* t_starts, const float* t_ends, int64_t t_stride, int S,
                   float* acc,
                   float* sdf, float* sdf_orig, float* sdf_grad, float* normal, float* features,
-                  float* weights, float* trans, void* stream);
+                  float* weights, float* trans, float* scratch, void* stream);
 /* Backward.  g_acc: [n_rays][TT_ACC] gradients of the accumulators.  Per-sample upstream
  * gradients (nullable): g_sdf [N], g_sdf_grad [N][3], g_normal [N][3], g_features [N][3],
  * g_weights [N].  rgb_grad_scale multiplies the colour gradient (rgb_grad_shrink,

@@ -41,6 +41,52 @@ inline dim3 blockDim_, gridDim_;
 inline float* smem_ = nullptr;
 inline std::barrier<>* bar_ = nullptr;
 inline std::atomic<int> or_flag_{0};
+inline std::barrier<>* gbar_[8] = {};
+inline float tmem_[128][512];
+
+// ---- tcgen05 emulation (see triplaneturbo_b200/csrc/tt_umma.cuh) ------------------------------------------
+inline uint32_t smem_off(const void* p) { return (uint32_t)((const char*)p - (const char*)smem_); }
+inline void group_sync(int g) { gbar_[g]->arrive_and_wait(); }
+inline void mbar_init(uint64_t* bar) { *bar = 0; }
+inline void mbar_arrive(uint32_t off) {
+    std::atomic_ref<uint64_t> r(*(uint64_t*)((char*)smem_ + off));
+    r.fetch_add(1);
+}
+inline void mbar_wait(uint32_t off, uint32_t parity) {
+    std::atomic_ref<uint64_t> r(*(uint64_t*)((char*)smem_ + off));
+    while ((r.load() & 1u) == parity) std::this_thread::yield();
+}
+inline float tf32(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
+inline void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
+    const int lane = (int)(addr >> 16) + (int)(threadIdx_.x & 31), col = (int)(addr & 0xffff);
+    for (int j = 0; j < 8; ++j) std::memcpy(&tmem_[lane][col + j], &v[j], 4);
+}
+inline void tmem_ld8(uint32_t addr, uint32_t (&v)[8]) {
+    const int lane = (int)(addr >> 16) + (int)(threadIdx_.x & 31), col = (int)(addr & 0xffff);
+    for (int j = 0; j < 8; ++j) std::memcpy(&v[j], &tmem_[lane][col + j], 4);
+}
+// D[128][N] (+)= A[128][K] * B[N][K]^T ; A hi at col a0, lo at col 64+a0, D at col 128 of the group's region
+inline void umma(uint32_t tmem, uint32_t a_col0, uint32_t bhi, uint32_t blo, uint32_t sbo, int N, int K, bool acc, int passes) {
+    const int c0 = (int)(tmem & 0xffff);
+    auto B = [&](uint32_t base, int n, int k) {
+        const uint32_t off = base + (n & 7) * 16 + (n >> 3) * sbo + (k >> 2) * 128 + (k & 3) * 4;
+        return tf32(*(const float*)((const char*)smem_ + off));
+    };
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            float d = acc ? tmem_[m][c0 + 128 + n] : 0.f;
+            for (int k0 = 0; k0 < K; k0 += 8) {
+                float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                for (int k = k0; k < k0 + 8; ++k) {
+                    const float ah = tf32(tmem_[m][c0 + a_col0 + k]), al = tf32(tmem_[m][c0 + 64 + a_col0 + k]);
+                    s3 += ah * B(bhi, n, k);
+                    if (passes == 3) { s1 += al * B(bhi, n, k); s2 += ah * B(blo, n, k); }
+                }
+                d = ((d + s1) + s2) + s3;
+            }
+            tmem_[m][c0 + 128 + n] = d;
+        }
+}
 }  // namespace tt_emul
 #define threadIdx tt_emul::threadIdx_
 #define blockIdx tt_emul::blockIdx_
@@ -68,6 +114,10 @@ inline float atomicAdd(float* addr, float v) {
     while (!r.compare_exchange_weak(old, old + v)) {}
     return old;
 }
+inline int atomicAdd(int* addr, int v) { std::atomic_ref<int> r(*addr); return r.fetch_add(v); }
+inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline void __trap() { std::abort(); }
 using std::max;
 using std::min;
 
@@ -78,6 +128,10 @@ enum { cudaSuccess = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 2; return cudaSuccess; }
 template <typename K> inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
 
 namespace tt_emul {
@@ -89,6 +143,11 @@ void launch(K kernel, dim3 grid, dim3 block, size_t smem_bytes, A... args) {
     smem_ = static_cast<float*>(std::align(16, smem_bytes, p, space));
     std::barrier<> bar(nthreads);
     bar_ = &bar; blockDim_ = block; gridDim_ = grid;
+    std::vector<std::unique_ptr<std::barrier<>>> groups;
+    for (unsigned g = 0; g < nthreads / 128 && g < 8; ++g) {
+        groups.emplace_back(new std::barrier<>(128));
+        gbar_[g] = groups.back().get();
+    }
     auto worker = [&](unsigned t) {
         threadIdx_.x = t % block.x; threadIdx_.y = (t / block.x) % block.y; threadIdx_.z = t / (block.x * block.y);
         for (unsigned bz = 0; bz < grid.z; ++bz)

@@ -51,10 +51,13 @@ class Emul:
         assert code == 0, f"{what}: {self.L.tt_last_error().decode()}"
 
     def config(self, C_, R, P, rays_per_cache=1, radius=1.0, bias=0.5, inv_std=None, car=1.0, near=0.1, far=4.0,
-               step=0.05):
+               step=0.05, flags=1):
         if inv_std is None:
             inv_std = float(np.exp(np.float32(0.4605) * np.float32(10.0)))
-        return _cabi.TTConfig(C_, R, P, rays_per_cache, radius, bias, inv_std, car, near, far, step)
+        return _cabi.TTConfig(C_, R, P, rays_per_cache, radius, bias, inv_std, car, near, far, step, flags)
+
+    def set_impl(self, impl):
+        self.ok(self.L.tt_set_impl(impl), "set_impl")
 
     def pack_weights(self, w, C_):
         wp = aligned_zeros(self.L.tt_wpack_floats(C_))
@@ -133,9 +136,11 @@ class Emul:
                    sdf_grad=np.zeros((N, 3), np.float32), normal=np.zeros((N, 3), np.float32),
                    features=np.zeros((N, 3), np.float32), weights=np.zeros(N, np.float32),
                    trans=np.zeros(N, np.float32))
+        scratch = np.zeros(self.L.tt_render_fwd_scratch_floats(n, S), np.float32)
         self.ok(self.L.tt_render_fwd(ptr(planes), ptr(wp), C.byref(cfg), ptr(o), ptr(d), n, ptr(t0), ptr(t1), S, S,
                                      *[ptr(out[k]) for k in ("acc", "sdf", "sdf_orig", "sdf_grad", "normal",
-                                                              "features", "weights", "trans")], None), "render_fwd")
+                                                              "features", "weights", "trans")], ptr(scratch), None),
+                "render_fwd")
         return out
 
     def render_bwd(self, planes, wp, cfg, rays_o, rays_d, t_starts, t_ends, fwd, g_acc, g_sdf=None, g_sdf_grad=None,

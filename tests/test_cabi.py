@@ -44,11 +44,11 @@ def test_size_queries_and_offsets(lib):
         assert lib.tt_wpack_floats(C_) > lib.tt_wgrad_floats(C_)
     assert lib.tt_wpack_floats(12) == 0
     assert lib.tt_render_bwd_scratch_floats(10, 7) == 490
-    assert lib.tt_sample_scratch_floats(10, 16) == 170
+    assert lib.tt_sample_scratch_floats(10, 16) == 340
 
 
 def test_argument_errors_are_reported_not_crashed(lib):
-    cfg = _cabi.TTConfig(12, 16, 1, 1, 1.0, 0.5, 100.0, 1.0, 0.1, 4.0, 0.05)      # unsupported C
+    cfg = _cabi.TTConfig(12, 16, 1, 1, 1.0, 0.5, 100.0, 1.0, 0.1, 4.0, 0.05, 0)      # unsupported C
     rc = lib.tt_geometry_fwd(None, None, C.byref(cfg), None, 0, 0, None, None, None, None, None, None, None)
     assert rc == -1 and b"channel" in lib.tt_last_error()
     rc = lib.tt_repack_planes(None, 1, 8, 0, 0, 8, 16, None, None)

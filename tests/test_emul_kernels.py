@@ -16,9 +16,11 @@ TOL = 1e-4      # north_star: 1e-4 on RGB / sigma
 GTOL = 2e-3     # gradients, relative to the tensor's max magnitude
 
 
-@pytest.fixture(scope="module")
-def em():
-    return Emul()
+@pytest.fixture(scope="module", params=[1, 0], ids=["tcgen05", "simt"])
+def em(request):
+    e = Emul()
+    e.set_impl(request.param)     # both kernel families run through the same checks
+    return e
 
 
 def np_w(w):

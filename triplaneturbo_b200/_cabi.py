@@ -20,7 +20,7 @@ class TTConfig(C.Structure):
     _fields_ = [("C", C.c_int32), ("R", C.c_int32), ("P", C.c_int32), ("rays_per_cache", C.c_int32),
                 ("radius", C.c_float), ("sdf_bias_radius", C.c_float), ("inv_std", C.c_float),
                 ("cos_anneal_ratio", C.c_float), ("near_plane", C.c_float), ("far_plane", C.c_float),
-                ("render_step_size", C.c_float)]
+                ("render_step_size", C.c_float), ("flags", C.c_int32)]
 
 
 _cfgp = C.POINTER(TTConfig)
@@ -30,6 +30,8 @@ SIGNATURES = {
     "tt_version": (C.c_int, []),
     "tt_last_error": (C.c_char_p, []),
     "tt_device_ok": (C.c_int, []),
+    "tt_set_impl": (C.c_int, [C.c_int]),
+    "tt_get_impl": (C.c_int, []),
     "tt_launch_count": (i64, []),
     "tt_profile_begin": (C.c_int, []),
     "tt_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),
@@ -44,7 +46,8 @@ SIGNATURES = {
     "tt_geometry_bwd": (C.c_int, [fp, fp, _cfgp, fp, i64] + [fp] * 4 + [fp, fp, fp, fp]),
     "tt_sample_scratch_floats": (C.c_size_t, [i64, C.c_int]),
     "tt_importance_sample": (C.c_int, [fp, fp, _cfgp, fp, fp, i64, C.c_int, C.c_int, fp, fp, fp, fp, fp]),
-    "tt_render_fwd": (C.c_int, [fp, fp, _cfgp, fp, fp, i64, fp, fp, i64, C.c_int] + [fp] * 8 + [fp]),
+    "tt_render_fwd_scratch_floats": (C.c_size_t, [i64, C.c_int]),
+    "tt_render_fwd": (C.c_int, [fp, fp, _cfgp, fp, fp, i64, fp, fp, i64, C.c_int] + [fp] * 8 + [fp, fp]),
     "tt_render_bwd_scratch_floats": (C.c_size_t, [i64, C.c_int]),
     "tt_render_bwd": (C.c_int, [fp, fp, _cfgp, fp, fp, i64, fp, fp, i64, C.c_int] + [fp] * 5 + [fp] * 6 +
                       [C.c_float, fp, fp, fp, fp, fp]),

@@ -1,6 +1,7 @@
 // Kernels + C ABI of libtriplane_b200.so (see include/triplane_b200.h).  sm_100a only, no CPU path.
-#include "tt_device.cuh"
 #include "../../include/triplane_b200.h"
+#include "tt_device.cuh"
+#include "tt_tc.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -12,6 +13,8 @@ using namespace tt;
 // host-side helpers
 // =====================================================================================================
 static thread_local char g_err[512] = "";
+static int g_impl = 1;      // 1: tcgen05 tensor-core kernels (tt_tc.cuh), 0: SIMT reference kernels (this file)
+static const size_t kMaxSmem = 227 * 1024;
 static std::atomic<int64_t> g_launches{0};
 
 static int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
@@ -75,6 +78,19 @@ static int set_smem(K kernel, size_t bytes) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(%zu B smem): %s", bytes, cudaGetErrorString(e)); return TT_E_CUDA; }
     return TT_OK;
+}
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+static unsigned tc_grid(int64_t n_points) {
+    const int64_t ctas = (n_points + TC_THREADS - 1) / TC_THREADS;
+    return (unsigned)(ctas < (int64_t)num_sms() ? (ctas < 1 ? 1 : ctas) : num_sms());
 }
 static inline size_t slab_bytes(int rows) { return (size_t)rows * ST * sizeof(float); }
 static inline int imax(int a, int b) { return a > b ? a : b; }
@@ -781,6 +797,12 @@ int tt_profile_end(char* buf, size_t cap) {
 #endif
     return TT_OK;
 }
+int tt_set_impl(int impl) {
+    if (impl != 0 && impl != 1) return fail(TT_E_ARG, "tt_set_impl: impl must be 0 (SIMT) or 1 (tcgen05)%s", "");
+    g_impl = impl;
+    return TT_OK;
+}
+int tt_get_impl(void) { return g_impl; }
 int tt_device_ok(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) { cudaGetLastError(); return 0; }
@@ -837,6 +859,34 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
     if (!aligned16(planes) || !aligned16(wpack)) return fail(TT_E_ALIGN, "planes/wpack must be 16-byte aligned%s", "");
     const int64_t N = (int64_t)cfg->P * M;
     if (N == 0) return TT_OK;
+    if (g_impl == 1 && !deformation && N < 2147483647LL) {
+        bool done = false;
+        TT_DISPATCH_C(cfg->C, {
+            const size_t smg_n = (size_t)GeoSmem<kC, true>::TOTAL * 4, smg = (size_t)GeoSmem<kC, false>::TOTAL * 4;
+            const size_t smt = (size_t)TexSmem<kC>::TOTAL * 4;
+            const bool want_n = normal || sdf_grad;
+            if ((want_n ? smg_n : smg) <= kMaxSmem && smt <= kMaxSmem) {
+                TcSrc src{}; src.mode = points ? 0 : 3; src.points = points; src.M = M; src.grid_res = grid_res;
+                if (sdf || sdf_orig || want_n) {
+                    if (want_n) {
+                        if (int e = set_smem(k_geo_tc<kC, true>, smg_n)) return e;
+                        TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg_n, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal);
+                    } else {
+                        if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
+                        TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal);
+                    }
+                    if (int e = check_launch("k_geo_tc")) return e;
+                }
+                if (features) {
+                    if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
+                    TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, (cudaStream_t)stream, planes, wpack, *cfg, src, N, features);
+                    if (int e = check_launch("k_tex_tc")) return e;
+                }
+                done = true;
+            }
+        });
+        if (done) return TT_OK;
+    }
     const int64_t blocks = (N + TPB - 1) / TPB;
     if (blocks > 2147483647LL) return fail(TT_E_ARG, "tt_geometry_fwd: too many points%s (%lld)", "", N);
     TT_DISPATCH_C(cfg->C, {
@@ -848,7 +898,7 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
     return check_launch("tt_geometry_fwd");
 }
 
-size_t tt_sample_scratch_floats(int64_t n_rays, int n_imp) { return (size_t)n_rays * (size_t)(n_imp + 1); }
+size_t tt_sample_scratch_floats(int64_t n_rays, int n_imp) { return 2 * (size_t)n_rays * (size_t)(n_imp + 1); }
 
 int tt_importance_sample(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
                          const float* rays_d, int64_t n_rays, int n_imp, int n_fine, const float* jitter0,
@@ -862,6 +912,27 @@ int tt_importance_sample(const float* planes, const float* wpack, const tt_confi
     if (!aligned16(planes) || !aligned16(wpack)) return fail(TT_E_ALIGN, "planes/wpack must be 16-byte aligned%s", "");
     if (n_rays <= 0) return TT_OK;
     const int64_t blocks = (n_rays + TPB - 1) / TPB;
+    if (g_impl == 1 && n_rays * n_imp < 2147483647LL) {
+        bool done = false;
+        TT_DISPATCH_C(cfg->C, {
+            const size_t smg = (size_t)GeoSmem<kC, false>::TOTAL * 4;
+            if (smg <= kMaxSmem) {
+                float* cdf = scratch;
+                float* sdf = scratch + (size_t)n_rays * (size_t)(n_imp + 1);
+                TcSrc src{}; src.mode = 2; src.rs = RaySrcT{rays_o, rays_d, nullptr, nullptr, 0, 1};
+                src.rays_per_cache = cfg->rays_per_cache; src.n_imp = n_imp; src.jitter0 = jitter0;
+                src.near_plane = cfg->near_plane; src.far_plane = cfg->far_plane;
+                const int64_t N = n_rays * n_imp;
+                if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
+                TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, (float*)nullptr, (float*)nullptr, (float*)nullptr);
+                if (int e = check_launch("k_geo_tc")) return e;
+                TT_LAUNCH(k_sampler_post, (unsigned)blocks, TPB, 0, (cudaStream_t)stream, *cfg, n_rays, n_imp, n_fine, (const float*)sdf, jitter0, jitter1, cdf, t_vals);
+                if (int e = check_launch("k_sampler_post")) return e;
+                done = true;
+            }
+        });
+        if (done) return TT_OK;
+    }
     TT_DISPATCH_C(cfg->C, {
         const size_t sm = slab_bytes(imax(kC, HID) + HID);
         if (int e = set_smem(k_importance_sample<kC>, sm)) return e;
@@ -880,10 +951,12 @@ static int check_rays(const char* who, const tt_config* cfg, const float* rays_o
     return TT_OK;
 }
 
+size_t tt_render_fwd_scratch_floats(int64_t n_rays, int S) { return (size_t)n_rays * (size_t)S * 9 + 16; }
+
 int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
                   const float* rays_d, int64_t n_rays, const float* t_starts, const float* t_ends, int64_t t_stride,
                   int S, float* acc, float* sdf, float* sdf_orig, float* sdf_grad, float* normal, float* features,
-                  float* weights, float* trans, void* stream) {
+                  float* weights, float* trans, float* scratch, void* stream) {
     if (int e = check_cfg(cfg)) return e;
     if (!planes || !wpack || !acc) return fail(TT_E_ARG, "tt_render_fwd: NULL pointer%s", "");
     if (int e = check_rays("tt_render_fwd", cfg, rays_o, rays_d, n_rays, t_starts, t_ends, t_stride, S)) return e;
@@ -891,6 +964,40 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
     if (n_rays <= 0) return TT_OK;
     const RaySrc rs{rays_o, rays_d, t_starts, t_ends, t_stride, S};
     const int64_t blocks = (n_rays + TPB - 1) / TPB;
+    if (g_impl == 1 && scratch && n_rays * S < 2147483647LL) {
+        bool done = false;
+        TT_DISPATCH_C(cfg->C, {
+            const size_t smg = (size_t)GeoSmem<kC, true>::TOTAL * 4, smt = (size_t)TexSmem<kC>::TOTAL * 4;
+            if (smg <= kMaxSmem && smt <= kMaxSmem) {
+                cudaStream_t st = (cudaStream_t)stream;
+                const int64_t N = n_rays * S;
+                float* p_sdf = sdf ? sdf : scratch;
+                float* p_grad = sdf_grad ? sdf_grad : scratch + N;
+                float* p_trans = trans ? trans : scratch + 4 * N;
+                float* p_feat = features ? features : scratch + 5 * N;
+                int* live = reinterpret_cast<int*>(scratch + 8 * N);
+                int* count = live + N;
+                const int all_live = (cfg->flags & TT_FLAG_ALL_FEATURES) ? 1 : 0;
+                const RaySrcT rt{rays_o, rays_d, t_starts, t_ends, t_stride, S};
+                TcSrc src{}; src.mode = 1; src.rs = rt; src.rays_per_cache = cfg->rays_per_cache;
+                if (cudaMemsetAsync(count, 0, sizeof(int), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
+                if (int e = set_smem(k_geo_tc<kC, true>, smg)) return e;
+                TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, src, N, p_sdf, sdf_orig, p_grad, (float*)nullptr);
+                if (int e = check_launch("k_geo_tc")) return e;
+                TT_LAUNCH(k_weights, (unsigned)blocks, TPB, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, acc, weights, p_trans, normal,
+                          all_live ? (float*)nullptr : p_feat, all_live ? (int*)nullptr : live, count, all_live);
+                if (int e = check_launch("k_weights")) return e;
+                if (!all_live) { src.index = live; src.count = count; }
+                if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
+                TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, src, N, p_feat);
+                if (int e = check_launch("k_tex_tc")) return e;
+                TT_LAUNCH(k_accum_rgb, (unsigned)blocks, TPB, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, (const float*)p_trans, (const float*)p_feat, acc);
+                if (int e = check_launch("k_accum_rgb")) return e;
+                done = true;
+            }
+        });
+        if (done) return TT_OK;
+    }
     TT_DISPATCH_C(cfg->C, {
         const size_t sm = slab_bytes(imax(kC, HID) + HID);
         if (int e = set_smem(k_render_fwd<kC>, sm)) return e;

@@ -1,0 +1,545 @@
+// Tensor-core (tcgen05) kernels of the forward path: point-list SDF decoder (+ analytic normal) and colour decoder,
+// plus the light per-ray kernels around them.  See tt_umma.cuh for the execution model.
+//
+// Forward pipeline (tt_render_fwd, impl = 1):
+//   k_geo_tc<C,true>   sdf, d sdf/dx at every sample                     (tensor cores, cooperative gathers)
+//   k_weights          per ray: NeuS alpha, transmittance, weights, all non-colour accumulators, live-sample list
+//   k_tex_tc<C>        colour features at the live samples (T > 0)        (tensor cores)
+//   k_accum_rgb        per ray: Σ w · sigmoid_mipnerf(features)
+// Sampler (tt_importance_sample, impl = 1):  k_geo_tc<C,false> on the proposal midpoints, then k_sampler_post.
+#pragma once
+#include "tt_device.cuh"
+#include "tt_umma.cuh"
+
+namespace tt {
+
+constexpr int TC_THREADS = 256;      // two groups of 128 per CTA share the weight tiles
+constexpr int TC_GROUPS = TC_THREADS / TC_GROUP;
+
+struct RaySrcT {
+    const float* rays_o; const float* rays_d;
+    const float* t_starts; const float* t_ends; int64_t t_stride; int S;
+};
+struct TcSrc {
+    int mode;                 // 0: explicit points, 1: ray samples (id = ray*S + i), 2: proposal midpoints
+                              // (id = ray*n_imp + j), 3: isosurface grid (id = prompt*res^3 + vertex)
+    const float* points; int64_t M;
+    RaySrcT rs; int rays_per_cache;
+    int n_imp; const float* jitter0; float near_plane, far_plane;
+    int grid_res;
+    const int* index; const int* count;     // optional compaction: slot -> id, *count live slots
+};
+
+__device__ __forceinline__ float quantile_s(int j, int n, bool strat, float b) {
+    return strat ? __fdiv_rn(__fadd_rn((float)j, b), (float)(n + 1)) : __fdiv_rn((float)j, (float)n);
+}
+__device__ __forceinline__ float stot_u(float s, float tmin, float tmax) {
+    return __fadd_rn(__fmul_rn(s, tmax), __fmul_rn(__fsub_rn(1.f, s), tmin));
+}
+__device__ __forceinline__ float grid_coord_tc(int i, int res) {
+    const float step = __fdiv_rn(1.f, (float)(res - 1));
+    float v = (i < res / 2) ? __fmul_rn((float)i, step) : __fsub_rn(1.f, __fmul_rn((float)(res - 1 - i), step));
+    return __fadd_rn(__fmul_rn(v, 2.f), -1.f);
+}
+__device__ __forceinline__ void tc_point(const TcSrc& s, int64_t id, float (&x)[3], int& prompt) {
+    if (s.mode == 0) {
+        x[0] = s.points[id * 3]; x[1] = s.points[id * 3 + 1]; x[2] = s.points[id * 3 + 2];
+        prompt = (int)(id / s.M);
+    } else if (s.mode == 3) {
+        const int64_t v = id % s.M; const int r = s.grid_res;
+        x[0] = grid_coord_tc((int)(v / ((int64_t)r * r)), r); x[1] = grid_coord_tc((int)((v / r) % r), r);
+        x[2] = grid_coord_tc((int)(v % r), r);
+        prompt = (int)(id / s.M);
+    } else {
+        int64_t ray; float tm;
+        if (s.mode == 1) {
+            ray = id / s.rs.S; const int i = (int)(id - ray * s.rs.S);
+            const float t0 = s.rs.t_starts[ray * s.rs.t_stride + i], t1 = s.rs.t_ends[ray * s.rs.t_stride + i];
+            tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+        } else {
+            ray = id / s.n_imp; const int j = (int)(id - ray * s.n_imp);
+            const bool strat = s.jitter0 != nullptr; const float b = strat ? s.jitter0[ray] : 0.f;
+            const float t0 = stot_u(quantile_s(j, s.n_imp, strat, b), s.near_plane, s.far_plane);
+            const float t1 = stot_u(quantile_s(j + 1, s.n_imp, strat, b), s.near_plane, s.far_plane);
+            tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(s.rs.rays_o[ray * 3 + a], __fmul_rn(s.rs.rays_d[ray * 3 + a], tm));
+        prompt = (int)(ray / s.rays_per_cache);
+    }
+}
+
+// ---- cooperative gather: 128 points x C channels, consecutive lanes read consecutive 16-byte chunks of a texel ---
+// tap table per point: int o[NT], float w[NT] (NT = 4 * NPL), prompt-plane base offset (in floats / 4) in pbase
+template <int C, int NPL>
+__device__ __forceinline__ void coop_gather(const float* __restrict__ planes, size_t ps, const int* tap_o,
+                                            const float* tap_w, const uint32_t* pbase, int plane0, float* stage, int tg) {
+    constexpr int U = C / 4, NT = 4 * NPL, SP = C + 4;
+#pragma unroll 1
+    for (int j = 0; j < U; ++j) {
+        const int item = tg + TC_GROUP * j;
+        const int pt = item / U, ch = item - pt * U;
+        const float* base = planes + (size_t)pbase[pt] * 6 * ps + (size_t)plane0 * ps + ch * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int o = tap_o[pt * NT + k * 4 + t];
+                if (o >= 0) {
+                    const float4 v = ldg4(base + k * ps + (size_t)o * C);
+                    const float ww = tap_w[pt * NT + k * 4 + t];
+                    s.x = fmaf(ww, v.x, s.x); s.y = fmaf(ww, v.y, s.y); s.z = fmaf(ww, v.z, s.z); s.w = fmaf(ww, v.w, s.w);
+                }
+            }
+            acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+        }
+        *reinterpret_cast<float4*>(stage + pt * SP + ch * 4) = acc;
+    }
+}
+
+// shared-memory plan of k_geo_tc (float offsets)
+template <int C, bool NORMAL>
+struct GeoSmem {
+    static constexpr int CP = (C + 15) / 16 * 16;
+    static constexpr int W1H = 0, W1L = W1H + 64 * C, W2H = W1L + 64 * C, W2L = W2H + 4096;
+    static constexpr int W2TH = W2L + 4096, W2TL = W2TH + (NORMAL ? 4096 : 0);
+    static constexpr int W1TH = W2TL + (NORMAL ? 4096 : 0), W1TL = W1TH + (NORMAL ? CP * 64 : 0);
+    static constexpr int W3 = W1TL + (NORMAL ? CP * 64 : 0);
+    static constexpr int GROUP0 = W3 + 64;
+    // per group
+    static constexpr int TAP_O = 0, TAP_W = TAP_O + 128 * 12, TAP_F = TAP_W + 128 * 12;      // ints, floats, factors
+    static constexpr int PBASE = TAP_F + (NORMAL ? 128 * 12 : 0);
+    static constexpr int NACC = PBASE + 128;
+    static constexpr int STAGE = NACC + (NORMAL ? 128 * 6 : 0);
+    static constexpr int GROUP_FLOATS = STAGE + 128 * (C + 4);
+    static constexpr int TOTAL = GROUP0 + TC_GROUPS * GROUP_FLOATS + 16;     // + mbarriers, tmem slot
+};
+
+template <int C, bool NORMAL>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restrict__ planes, const float* __restrict__ wp,
+                                                         tt_config cfg, TcSrc src, int64_t N, float* sdf_o,
+                                                         float* sdf_orig_o, float* grad_o, float* normal_o) {
+    TT_SHARED(smem);
+    using L = GeoSmem<C, NORMAL>;
+    constexpr int CP = L::CP, SP = C + 4;
+    const int tid = threadIdx.x, group = tid / TC_GROUP, tg = tid % TC_GROUP, warp = tid >> 5;
+    const WOff wo = woff(C);
+    // ---- one-time setup: weight tiles (tf32 hi/lo, canonical K-major), mbarriers, TMEM ------------------------
+    btile_fill(smem + L::W1H, smem + L::W1L, 64, C, [&](int n, int k) { return __ldg(wp + wo.w1s + n * C + k); }, tid, TC_THREADS);
+    btile_fill(smem + L::W2H, smem + L::W2L, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2s + n * 64 + k); }, tid, TC_THREADS);
+    if (NORMAL) {
+        btile_fill(smem + L::W2TH, smem + L::W2TL, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2s + k * 64 + n); }, tid, TC_THREADS);
+        btile_fill(smem + L::W1TH, smem + L::W1TL, CP, 64, [&](int n, int k) { return n < C ? __ldg(wp + wo.w1s + k * C + n) : 0.f; }, tid, TC_THREADS);
+    }
+    if (tid < 64) smem[L::W3 + tid] = __ldg(wp + wo.w3s + tid);
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::GROUP0 + TC_GROUPS * L::GROUP_FLOATS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + TC_GROUPS);
+    if (tid == 0) for (int g = 0; g < TC_GROUPS; ++g) mbar_init(mbars + g);
+    if (warp == 0) tmem_alloc_warp(tmem_slot, 512);
+    async_proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    Umma u;
+    u.tmem = *tmem_slot + (uint32_t)group * TC_COLS_PER_GROUP;
+    u.lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    u.mbar = smem_u32(mbars + group); u.phase = 0; u.group = group;
+    const bool leader = tg == 0;
+    const BTile bW1 = btile_make(smem + L::W1H, smem + L::W1L, 64, C);
+    const BTile bW2 = btile_make(smem + L::W2H, smem + L::W2L, 64, 64);
+    const BTile bW2T = btile_make(smem + L::W2TH, smem + L::W2TL, 64, 64);
+    const BTile bW1T = btile_make(smem + L::W1TH, smem + L::W1TL, CP, 64);
+    float* gs = smem + L::GROUP0 + group * L::GROUP_FLOATS;
+    int* tap_o = reinterpret_cast<int*>(gs + L::TAP_O);
+    float* tap_w = gs + L::TAP_W;
+    float* tap_f = gs + L::TAP_F;
+    uint32_t* pbase = reinterpret_cast<uint32_t*>(gs + L::PBASE);
+    float* nacc = gs + L::NACC;
+    float* stage = gs + L::STAGE;
+    const size_t ps = (size_t)cfg.R * cfg.R * C;
+    const int64_t n_live = src.count ? (int64_t)*src.count : N;
+    const int64_t n_tiles = (n_live + TC_GROUP - 1) / TC_GROUP;
+    const float* w3 = smem + L::W3;
+
+    for (int64_t tile = (int64_t)blockIdx.x * TC_GROUPS + group; tile < n_tiles; tile += (int64_t)gridDim.x * TC_GROUPS) {
+        const int64_t slot = tile * TC_GROUP + tg;
+        const bool valid = slot < n_live;
+        const int64_t id = valid ? (src.index ? (int64_t)src.index[slot] : slot) : 0;
+        float x[3] = {0.f, 0.f, 0.f}; int prompt = 0;
+        Taps tp[3];
+        if (valid) {
+            tc_point(src, id, x, prompt);
+            float p[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) tp[k] = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                tap_o[tg * 12 + k * 4 + t] = valid ? tp[k].o[t] : -1;
+                tap_w[tg * 12 + k * 4 + t] = valid ? tp[k].w[t] : 0.f;
+            }
+            if (NORMAL) {
+                tap_f[tg * 12 + k * 4 + 0] = valid ? tp[k].wx0 : 0.f; tap_f[tg * 12 + k * 4 + 1] = valid ? tp[k].wx1 : 0.f;
+                tap_f[tg * 12 + k * 4 + 2] = valid ? tp[k].wy0 : 0.f; tap_f[tg * 12 + k * 4 + 3] = valid ? tp[k].wy1 : 0.f;
+            }
+        }
+        pbase[tg] = (uint32_t)prompt;
+        if (NORMAL) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) nacc[tg * 6 + q] = 0.f;
+        }
+        group_sync(group);
+        coop_gather<C, 3>(planes, ps, tap_o, tap_w, pbase, 0, stage, tg);
+        group_sync(group);
+        // ---- SDF MLP on tensor cores ----------------------------------------------------------------------------
+        float d[64];
+        uint64_t m1 = 0, m2 = 0;
+        {
+            float e[C];
+#pragma unroll
+            for (int c = 0; c < C; c += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(stage + tg * SP + c);
+                e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
+            }
+            umma_layer<C, 64, 3>(u, leader, e, bW1, d);
+        }
+#pragma unroll
+        for (int j = 0; j < 64; ++j) { const bool on = d[j] > 0.f; m1 |= (uint64_t)on << j; d[j] = on ? d[j] : 0.f; }
+        {
+            float h[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) h[j] = d[j];
+            umma_layer<64, 64, 3>(u, leader, h, bW2, d);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) { const bool on = d[j] > 0.f; m2 |= (uint64_t)on << j; s = fmaf(on ? d[j] : 0.f, w3[j], s); }
+        const float nrm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+        if (valid) {
+            if (sdf_orig_o) sdf_orig_o[id] = s;
+            if (sdf_o) sdf_o[id] = s + (nrm - cfg.sdf_bias_radius);
+        }
+        if (NORMAL) {
+            {   // unit-seed adjoint: a2 = m2 ⊙ w3 ; a1 = m1 ⊙ (W2ᵀ a2) ; de = W1ᵀ a1
+                float a[64];
+#pragma unroll
+                for (int j = 0; j < 64; ++j) a[j] = ((m2 >> j) & 1ull) ? w3[j] : 0.f;
+                umma_layer<64, 64, 3>(u, leader, a, bW2T, d);
+#pragma unroll
+                for (int j = 0; j < 64; ++j) a[j] = ((m1 >> j) & 1ull) ? d[j] : 0.f;
+                float de[CP];
+                umma_layer<64, CP, 3>(u, leader, a, bW1T, de);
+#pragma unroll
+                for (int c = 0; c < C; c += 4)
+                    *reinterpret_cast<float4*>(stage + tg * SP + c) = make_float4(de[c], de[c + 1], de[c + 2], de[c + 3]);
+            }
+            group_sync(group);
+            {   // cooperative pass: d(de · f_k)/d(ix,iy) per plane, reduced over channel chunks with shared atomics
+                constexpr int U = C / 4;
+#pragma unroll 1
+                for (int j = 0; j < U; ++j) {
+                    const int item = tg + TC_GROUP * j;
+                    const int pt = item / U, ch = item - pt * U;
+                    const float4 dv = *reinterpret_cast<const float4*>(stage + pt * SP + ch * 4);
+                    const float* base = planes + (size_t)pbase[pt] * 6 * ps + ch * 4;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        float A[4];
+                        bool any = false;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int o = tap_o[pt * 12 + k * 4 + t];
+                            float v = 0.f;
+                            if (o >= 0) {
+                                const float4 q = ldg4(base + k * ps + (size_t)o * C);
+                                v = dv.x * q.x + dv.y * q.y + dv.z * q.z + dv.w * q.w;
+                                any = true;
+                            }
+                            A[t] = v;
+                        }
+                        if (any) {
+                            const float wx0 = tap_f[pt * 12 + k * 4], wx1 = tap_f[pt * 12 + k * 4 + 1];
+                            const float wy0 = tap_f[pt * 12 + k * 4 + 2], wy1 = tap_f[pt * 12 + k * 4 + 3];
+                            atomicAdd(nacc + pt * 6 + k * 2, (A[1] - A[0]) * wy0 + (A[3] - A[2]) * wy1);
+                            atomicAdd(nacc + pt * 6 + k * 2 + 1, (A[2] - A[0]) * wx0 + (A[3] - A[1]) * wx1);
+                        }
+                    }
+                }
+            }
+            group_sync(group);
+            if (valid && (grad_o || normal_o)) {
+                float gm[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { gm[plane_ax(k)] += nacc[tg * 6 + k * 2]; gm[plane_ay(k)] += nacc[tg * 6 + k * 2 + 1]; }
+                const float scale = 0.5f * (float)cfg.R / cfg.radius;
+                const float inv = nrm > 0.f ? 1.f / nrm : 0.f;
+                float g[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) g[a] = gm[a] * scale + x[a] * inv;
+                if (grad_o) { grad_o[id * 3] = g[0]; grad_o[id * 3 + 1] = g[1]; grad_o[id * 3 + 2] = g[2]; }
+                if (normal_o) {
+                    float n[3], len; normalize3(g, n, len);
+                    normal_o[id * 3] = n[0]; normal_o[id * 3 + 1] = n[1]; normal_o[id * 3 + 2] = n[2];
+                }
+            }
+        }
+        group_sync(group);     // tap table / stage are rewritten by the next tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_warp(*tmem_slot, 512);
+}
+
+// ---- colour decoder at a list of samples -----------------------------------------------------------------------
+template <int C>
+struct TexSmem {
+    static constexpr int W1H = 0, W1L = W1H + 3 * 64 * C, W2H = W1L + 3 * 64 * C, W2L = W2H + 4096, W3 = W2L + 4096;
+    static constexpr int GROUP0 = W3 + 192;
+    static constexpr int TAP_O = 0, TAP_W = TAP_O + 128 * 4, PBASE = TAP_W + 128 * 4, STAGE = PBASE + 128;
+    static constexpr int GROUP_FLOATS = STAGE + 128 * (C + 4);
+    static constexpr int TOTAL = GROUP0 + TC_GROUPS * GROUP_FLOATS + 16;
+};
+
+template <int C>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp,
+                                                         tt_config cfg, TcSrc src, int64_t N, float* feat_o) {
+    TT_SHARED(smem);
+    using L = TexSmem<C>;
+    constexpr int SP = C + 4;
+    const int tid = threadIdx.x, group = tid / TC_GROUP, tg = tid % TC_GROUP, warp = tid >> 5;
+    const WOff wo = woff(C);
+    for (int k = 0; k < 3; ++k)      // W1f as three [64][C] K-major tiles (one per texture plane)
+        btile_fill(smem + L::W1H + k * 64 * C, smem + L::W1L + k * 64 * C, 64, C,
+                   [&](int n, int kk) { return __ldg(wp + wo.w1f + n * 3 * C + k * C + kk); }, tid, TC_THREADS);
+    btile_fill(smem + L::W2H, smem + L::W2L, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2f + n * 64 + k); }, tid, TC_THREADS);
+    if (tid < 192) smem[L::W3 + tid] = __ldg(wp + wo.w3f + tid);
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::GROUP0 + TC_GROUPS * L::GROUP_FLOATS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + TC_GROUPS);
+    if (tid == 0) for (int g = 0; g < TC_GROUPS; ++g) mbar_init(mbars + g);
+    if (warp == 0) tmem_alloc_warp(tmem_slot, 512);
+    async_proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    Umma u;
+    u.tmem = *tmem_slot + (uint32_t)group * TC_COLS_PER_GROUP;
+    u.lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    u.mbar = smem_u32(mbars + group); u.phase = 0; u.group = group;
+    const bool leader = tg == 0;
+    BTile bW1[3];
+    for (int k = 0; k < 3; ++k) bW1[k] = btile_make(smem + L::W1H + k * 64 * C, smem + L::W1L + k * 64 * C, 64, C);
+    const BTile bW2 = btile_make(smem + L::W2H, smem + L::W2L, 64, 64);
+    float* gs = smem + L::GROUP0 + group * L::GROUP_FLOATS;
+    int* tap_o = reinterpret_cast<int*>(gs + L::TAP_O);
+    float* tap_w = gs + L::TAP_W;
+    uint32_t* pbase = reinterpret_cast<uint32_t*>(gs + L::PBASE);
+    float* stage = gs + L::STAGE;
+    const float* w3 = smem + L::W3;
+    const size_t ps = (size_t)cfg.R * cfg.R * C;
+    const int64_t n_live = src.count ? (int64_t)*src.count : N;
+    const int64_t n_tiles = (n_live + TC_GROUP - 1) / TC_GROUP;
+
+    for (int64_t tile = (int64_t)blockIdx.x * TC_GROUPS + group; tile < n_tiles; tile += (int64_t)gridDim.x * TC_GROUPS) {
+        const int64_t slot = tile * TC_GROUP + tg;
+        const bool valid = slot < n_live;
+        const int64_t id = valid ? (src.index ? (int64_t)src.index[slot] : slot) : 0;
+        float p[3] = {0.f, 0.f, 0.f}; int prompt = 0;
+        if (valid) {
+            float x[3];
+            tc_point(src, id, x, prompt);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
+        }
+        pbase[tg] = (uint32_t)prompt;
+        float d[64];
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+            Taps t;
+            if (valid) t = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { tap_o[tg * 4 + q] = valid ? t.o[q] : -1; tap_w[tg * 4 + q] = valid ? t.w[q] : 0.f; }
+            group_sync(group);
+            coop_gather<C, 1>(planes, ps, tap_o, tap_w, pbase, 3 + k, stage, tg);
+            group_sync(group);
+            float e[C];
+#pragma unroll
+            for (int c = 0; c < C; c += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(stage + tg * SP + c);
+                e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
+            }
+            if (k > 0) umma_wait(u);          // previous chunk's MMAs are done reading A
+            umma_put_A<C>(u, e);
+            group_sync(group);
+            if (leader) { umma_mma<3>(u, bW1[k], C, k > 0); umma_commit(u); }
+        }
+        umma_wait(u);
+        umma_get_D<64>(u, d);
+        {
+            float h[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) h[j] = fmaxf(d[j], 0.f);
+            umma_layer<64, 64, 3>(u, leader, h, bW2, d);
+        }
+        float f[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            const float h = fmaxf(d[j], 0.f);
+            f[0] = fmaf(h, w3[j], f[0]); f[1] = fmaf(h, w3[64 + j], f[1]); f[2] = fmaf(h, w3[128 + j], f[2]);
+        }
+        if (valid) { feat_o[id * 3] = f[0]; feat_o[id * 3 + 1] = f[1]; feat_o[id * 3 + 2] = f[2]; }
+        group_sync(group);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_warp(*tmem_slot, 512);
+}
+
+// ---- per-ray NeuS alpha + compositing of everything that does not need colour --------------------------------------
+// Reads per-sample sdf / sdf_grad, writes trans (and weights, normal if requested), the non-colour accumulators and
+// the list of live samples (transmittance > 0), whose colour is the only one that can reach the image or a gradient.
+__global__ void __launch_bounds__(128) k_weights(tt_config cfg, RaySrcT rs, int64_t n_rays, const float* __restrict__ sdf,
+                                                const float* __restrict__ grad, float* __restrict__ acc_o,
+                                                float* weights_o, float* trans_o, float* normal_o, float* feat_zero,
+                                                int* live_idx, int* live_count, int all_live) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active_ray = ray < n_rays;
+    const int64_t r = active_ray ? ray : 0;
+    const float d[3] = {rs.rays_d[r * 3], rs.rays_d[r * 3 + 1], rs.rays_d[r * 3 + 2]};
+    const float* t0p = rs.t_starts + r * rs.t_stride;
+    const float* t1p = rs.t_ends + r * rs.t_stride;
+    const int S = rs.S;
+    float T = 1.f, opac = 0.f, depth = 0.f, nsum[3] = {0.f, 0.f, 0.f}, wsum = 0.f, mean = 0.f, m2 = 0.f, eik = 0.f;
+    for (int i = 0; i < S; ++i) {
+        bool live = false;
+        const int64_t si = r * S + i;
+        if (active_ray) {
+            const float t0 = t0p[i], t1 = t1p[i];
+            const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f), dt = __fsub_rn(t1, t0);
+            const float g[3] = {grad[si * 3], grad[si * 3 + 1], grad[si * 3 + 2]};
+            float n[3], len; normalize3(g, n, len);
+            const AlphaTerms at = neus_alpha(sdf[si], n, d, dt, cfg.inv_std, cfg.cos_anneal_ratio);
+            eik += (len - 1.f) * (len - 1.f);
+            const float w = T * at.alpha;
+            opac += w; depth = fmaf(w, tm, depth);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) nsum[a] = fmaf(w, n[a], nsum[a]);
+            const float wn = wsum + w;
+            if (wn > 0.f) { const float dl = tm - mean; mean += (w / wn) * dl; m2 += w * dl * (tm - mean); }
+            wsum = wn;
+            if (weights_o) weights_o[si] = w;
+            if (trans_o) trans_o[si] = T;
+            if (normal_o) { normal_o[si * 3] = n[0]; normal_o[si * 3 + 1] = n[1]; normal_o[si * 3 + 2] = n[2]; }
+            live = all_live || T > 0.f;
+            if (!live && feat_zero) { feat_zero[si * 3] = 0.f; feat_zero[si * 3 + 1] = 0.f; feat_zero[si * 3 + 2] = 0.f; }
+            T *= (1.f - at.alpha);
+        }
+        if (live_idx) {     // warp-aggregated append of the live samples of this step
+#ifndef TT_EMUL
+            const unsigned m = __ballot_sync(0xffffffffu, live);
+            if (m) {
+                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(live_count, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (live) live_idx[base + __popc(m & ((1u << lane) - 1u))] = (int)si;
+            }
+#else
+            if (live) live_idx[atomicAdd(live_count, 1)] = (int)si;
+#endif
+        }
+    }
+    if (active_ray) {
+        float* a = acc_o + ray * TT_ACC;
+        a[0] = opac; a[1] = depth; a[2] = 0.f; a[3] = 0.f; a[4] = 0.f;
+        a[5] = m2 + wsum * (mean - depth) * (mean - depth);
+        a[6] = nsum[0]; a[7] = nsum[1]; a[8] = nsum[2]; a[9] = eik;
+    }
+}
+
+// rgb accumulator: Σ_i (T_i alpha_i) sigmoid_mipnerf(f_i); weights are recomputed from trans (w = T - T_next)
+__global__ void __launch_bounds__(128) k_accum_rgb(tt_config cfg, RaySrcT rs, int64_t n_rays, const float* __restrict__ sdf,
+                                                  const float* __restrict__ grad, const float* __restrict__ trans,
+                                                  const float* __restrict__ feat, float* __restrict__ acc_o) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    const float d[3] = {rs.rays_d[ray * 3], rs.rays_d[ray * 3 + 1], rs.rays_d[ray * 3 + 2]};
+    const float* t0p = rs.t_starts + ray * rs.t_stride;
+    const float* t1p = rs.t_ends + ray * rs.t_stride;
+    const int S = rs.S;
+    float rgb[3] = {0.f, 0.f, 0.f};
+    for (int i = 0; i < S; ++i) {
+        const int64_t si = ray * S + i;
+        const float T = trans[si];
+        if (T <= 0.f) break;                     // transmittance is non-increasing along the ray
+        const float dt = __fsub_rn(t1p[i], t0p[i]);
+        const float g[3] = {grad[si * 3], grad[si * 3 + 1], grad[si * 3 + 2]};
+        float n[3], len; normalize3(g, n, len);
+        const float w = T * neus_alpha(sdf[si], n, d, dt, cfg.inv_std, cfg.cos_anneal_ratio).alpha;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) rgb[a] = fmaf(w, sigmoid_mipnerf(feat[si * 3 + a]), rgb[a]);
+    }
+    acc_o[ray * TT_ACC + 2] = rgb[0]; acc_o[ray * TT_ACC + 3] = rgb[1]; acc_o[ray * TT_ACC + 4] = rgb[2];
+}
+
+// importance sampler, stage 2: proposal sdf [n_rays][n_imp] -> density -> cdf -> inverse-CDF draws -> sorted edges
+__global__ void __launch_bounds__(128) k_sampler_post(tt_config cfg, int64_t n_rays, int n_imp, int n_fine,
+                                                     const float* __restrict__ sdf, const float* __restrict__ jit0,
+                                                     const float* __restrict__ jit1, float* __restrict__ cdf,
+                                                     float* __restrict__ t_vals) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    const bool strat = jit0 != nullptr;
+    const float b0 = strat ? jit0[ray] : 0.f, b1 = strat ? jit1[ray] : 0.f;
+    const float step = cfg.render_step_size;
+    float run = 0.f;
+    float t_lo = stot_u(quantile_s(0, n_imp, strat, b0), cfg.near_plane, cfg.far_plane);
+    for (int j = 0; j < n_imp; ++j) {
+        const float t_hi = stot_u(quantile_s(j + 1, n_imp, strat, b0), cfg.near_plane, cfg.far_plane);
+        cdf[(size_t)j * n_rays + ray] = 1.f - expf(-run);
+        const float s = sdf[ray * n_imp + j];
+        const float pc = sigmoidf((s + step * 0.5f) * cfg.inv_std), nc = sigmoidf((s - step * 0.5f) * cfg.inv_std);
+        const float alpha = fminf(fmaxf((pc - nc + 1e-5f) / (pc + 1e-5f), 0.f), 1.f);
+        run += (alpha / step) * (t_hi - t_lo);
+        t_lo = t_hi;
+    }
+    cdf[(size_t)n_imp * n_rays + ray] = 1.f;
+    const int n_in = n_imp + 1, n_out = n_imp + n_fine + 2;
+    float* out = t_vals + (size_t)ray * n_out;
+    int k = 0; float last = -3.0e38f;
+    auto emit = [&](float v) {
+        if (v >= last) { out[k] = v; last = v; }
+        else { int j = k; while (j > 0 && out[j - 1] > v) { out[j] = out[j - 1]; --j; } out[j] = v; }
+        ++k;
+    };
+    int a = 0;
+    float ta = stot_u(quantile_s(0, n_imp, strat, b0), cfg.near_plane, cfg.far_plane);
+    int p = 0;
+    for (int j = 0; j <= n_fine; ++j) {
+        const float uq = quantile_s(j, n_fine, strat, b1);
+        while (p < n_in && cdf[(size_t)p * n_rays + ray] <= uq) ++p;
+        const int pc = min(max(p, 1), n_in - 1);
+        const float c0 = cdf[(size_t)(pc - 1) * n_rays + ray], c1 = cdf[(size_t)pc * n_rays + ray];
+        const float v0 = quantile_s(pc - 1, n_imp, strat, b0), v1 = quantile_s(pc, n_imp, strat, b0);
+        const float den = __fsub_rn(c1, c0);
+        float fr = den > 0.f ? __fdiv_rn(__fsub_rn(uq, c0), den) : 0.f;
+        fr = fminf(fmaxf(fr, 0.f), 1.f);
+        const float tf = stot_u(__fadd_rn(v0, __fmul_rn(fr, __fsub_rn(v1, v0))), cfg.near_plane, cfg.far_plane);
+        while (a < n_in && ta <= tf) {
+            emit(ta); ++a;
+            if (a < n_in) ta = stot_u(quantile_s(a, n_imp, strat, b0), cfg.near_plane, cfg.far_plane);
+        }
+        emit(tf);
+    }
+    while (a < n_in) {
+        emit(ta); ++a;
+        if (a < n_in) ta = stot_u(quantile_s(a, n_imp, strat, b0), cfg.near_plane, cfg.far_plane);
+    }
+}
+
+}  // namespace tt

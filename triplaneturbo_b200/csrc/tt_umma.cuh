@@ -1,0 +1,203 @@
+// tcgen05 (5th-gen tensor core) primitives for the decoder-MLP layers, sm_100a.
+//
+// Usage model ("thread = point, tensor core = layer"): a group of 128 threads owns a tile of 128 sample points;
+// thread i owns point i == TMEM lane i.  One decoder layer  Y[128][N] = X[128][K] · Wᵀ  is
+//   1. every thread splits its activation row into tf32 hi/lo parts and writes them to TMEM (tcgen05.st),
+//   2. one thread issues the K/8 x 3 tcgen05.mma (3xTF32: lo·hi + hi·lo + hi·hi, A from TMEM, W from shared memory
+//      in the canonical K-major no-swizzle layout) and commits to an mbarrier,
+//   3. every thread waits on the mbarrier and reads its output row back (tcgen05.ld).
+// The 3xTF32 split keeps ~1e-6 relative accuracy (measured, tools/umma_probe.cu), which the NeuS alpha needs
+// (inv_std = 100 multiplies SDF error inside a sigmoid).
+//
+// Under TT_EMUL (host emulation for tests/emul) the same API is implemented with plain loops.
+#pragma once
+#include <stdint.h>
+
+namespace tt {
+
+constexpr int TC_GROUP = 128;          // threads (= points = TMEM lanes) per tile
+constexpr uint32_t TC_COL_AHI = 0;     // TMEM column offsets inside a group's 256-column region
+constexpr uint32_t TC_COL_ALO = 64;
+constexpr uint32_t TC_COL_D = 128;
+constexpr uint32_t TC_COLS_PER_GROUP = 256;
+constexpr uint32_t TC_LBO = 128;       // bytes between the 16-byte K-chunks of a core-matrix row group
+
+// A weight matrix as MMA operand B: element (n, k) of the N x K (K-major) tile, tf32 hi and lo parts.
+struct BTile {
+    uint32_t hi, lo;     // shared-memory byte addresses (emulation: byte offsets into the block's smem)
+    uint32_t sbo;        // bytes between 8-row groups
+    int N, K;
+};
+__host__ __device__ inline int btile_floats(int N, int K) { return N * K; }
+__device__ __forceinline__ int btile_off(int n, int k, int K) {     // float offset of element (n,k)
+    return ((n & 7) * 16 + (n >> 3) * ((K >> 2) * 128) + (k >> 2) * 128 + (k & 3) * 4) >> 2;
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+struct Umma {
+    uint32_t tmem;        // TMEM address of column 0 of this group's region (lane field 0)
+    uint32_t lane_base;   // (warp % 4) * 32 << 16 : the TMEM lanes this warp may touch
+    uint32_t mbar;        // shared address of the group's mbarrier
+    uint32_t phase;
+    int group;
+};
+
+#ifndef TT_EMUL
+// ======================================================================================== device (sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void group_sync(int group) {      // named barrier over the group's 128 threads
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(TC_GROUP) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void async_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc_warp(uint32_t* slot, uint32_t ncols) {     // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_warp(uint32_t base, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int N) {      // M = 128, fp32 accumulate, K-major A and B
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_issue(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+        ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+// D (+)= A · Bᵀ over K (multiple of 8); issued by ONE thread.  PASSES = 3: 3xTF32, 1: hi·hi only.
+template <int PASSES>
+__device__ __forceinline__ void umma_mma(const Umma& u, const BTile& b, int K, bool accumulate, uint32_t a_col0 = 0) {
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_tf32(b.N);
+    const uint32_t d = u.tmem + TC_COL_D;
+    for (int ks = 0; ks < K / 8; ++ks) {
+        const uint32_t acc0 = (accumulate || ks > 0) ? 1u : 0u;
+        const uint64_t dh = umma_desc(b.hi + ks * 2 * TC_LBO, TC_LBO, b.sbo);
+        if (PASSES == 3) {
+            const uint64_t dl = umma_desc(b.lo + ks * 2 * TC_LBO, TC_LBO, b.sbo);
+            umma_issue(d, u.tmem + TC_COL_ALO + a_col0 + ks * 8, dh, idesc, acc0);
+            umma_issue(d, u.tmem + TC_COL_AHI + a_col0 + ks * 8, dl, idesc, 1u);
+            umma_issue(d, u.tmem + TC_COL_AHI + a_col0 + ks * 8, dh, idesc, 1u);
+        } else {
+            umma_issue(d, u.tmem + TC_COL_AHI + a_col0 + ks * 8, dh, idesc, acc0);
+        }
+    }
+}
+__device__ __forceinline__ void umma_commit(const Umma& u) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u.mbar) : "memory");
+}
+__device__ __forceinline__ void umma_wait(Umma& u) {          // all threads of the group
+    uint32_t done = 0;
+    for (int it = 0; it < (1 << 24) && !done; ++it)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(u.mbar), "r"(u.phase) : "memory");
+    if (!done) __trap();                                       // never hang the GPU: abort the kernel instead
+    u.phase ^= 1u;
+    tc_fence_after();
+}
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+#else
+// ======================================================================================== host emulation
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return tt_emul::smem_off(p); }
+__device__ __forceinline__ void group_sync(int group) { tt_emul::group_sync(group); }
+__device__ __forceinline__ void tc_fence_before() {}
+__device__ __forceinline__ void tc_fence_after() {}
+__device__ __forceinline__ void async_proxy_fence() {}
+__device__ __forceinline__ void tmem_alloc_warp(uint32_t* slot, uint32_t) { *slot = 0; }
+__device__ __forceinline__ void tmem_dealloc_warp(uint32_t, uint32_t) {}
+__device__ __forceinline__ void mbar_init(uint64_t* bar) { tt_emul::mbar_init(bar); }
+template <int PASSES>
+__device__ __forceinline__ void umma_mma(const Umma& u, const BTile& b, int K, bool accumulate, uint32_t a_col0 = 0) {
+    tt_emul::umma(u.tmem, a_col0, b.hi, b.lo, b.sbo, b.N, K, accumulate, PASSES);
+}
+__device__ __forceinline__ void umma_commit(const Umma& u) { tt_emul::mbar_arrive(u.mbar); }
+__device__ __forceinline__ void umma_wait(Umma& u) { tt_emul::mbar_wait(u.mbar, u.phase); u.phase ^= 1u; }
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) { tt_emul::tmem_st8(addr, v); }
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&v)[8]) { tt_emul::tmem_ld8(addr, v); }
+__device__ __forceinline__ void tmem_wait_st() {}
+__device__ __forceinline__ void tmem_wait_ld() {}
+#endif
+
+// ---- group-level layer steps ---------------------------------------------------------------------------------
+// this thread's activation row x[0..K) -> TMEM (tf32 hi at A_hi, exact remainder at A_lo)
+template <int K>
+__device__ __forceinline__ void umma_put_A(const Umma& u, const float (&x)[K], uint32_t col0 = 0) {
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float h = tf32_hi(x[k0 + j]);
+            hi[j] = __float_as_uint(h);
+            lo[j] = __float_as_uint(x[k0 + j] - h);
+        }
+        tmem_st8(u.tmem + u.lane_base + TC_COL_AHI + col0 + k0, hi);
+        tmem_st8(u.tmem + u.lane_base + TC_COL_ALO + col0 + k0, lo);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+}
+// this thread's output row d[0..N) <- TMEM
+template <int N>
+__device__ __forceinline__ void umma_get_D(const Umma& u, float (&d)[N]) {
+#pragma unroll
+    for (int n0 = 0; n0 < N; n0 += 8) {
+        uint32_t v[8];
+        tmem_ld8(u.tmem + u.lane_base + TC_COL_D + n0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[n0 + j] = __uint_as_float(v[j]);
+    }
+    tmem_wait_ld();
+    tc_fence_before();
+}
+// one full layer: put A, barrier, one thread issues + commits, everybody waits, get D
+template <int K, int N, int PASSES>
+__device__ __forceinline__ void umma_layer(Umma& u, bool leader, const float (&x)[K], const BTile& b, float (&d)[N]) {
+    umma_put_A<K>(u, x);
+    group_sync(u.group);
+    if (leader) { umma_mma<PASSES>(u, b, K, false); umma_commit(u); }
+    umma_wait(u);
+    umma_get_D<N>(u, d);
+}
+
+// cooperative fill of a B tile from a row-major source: element (n,k) = src(n,k)
+template <typename F>
+__device__ __forceinline__ void btile_fill(float* hi, float* lo, int N, int K, F src, int tid, int nthreads) {
+    for (int i = tid; i < N * K; i += nthreads) {
+        const int n = i / K, k = i - n * K;
+        const float w = src(n, k);
+        const float h = tf32_hi(w);
+        const int off = btile_off(n, k, K);
+        hi[off] = h;
+        lo[off] = w - h;
+    }
+}
+__device__ __forceinline__ BTile btile_make(const float* hi, const float* lo, int N, int K) {
+    BTile b; b.hi = smem_u32(hi); b.lo = smem_u32(lo); b.sbo = (uint32_t)(K >> 2) * 128u; b.N = N; b.K = K;
+    return b;
+}
+
+}  // namespace tt

@@ -52,9 +52,19 @@ def _need(t: Tensor, name: str) -> Tensor:
     return t.contiguous()
 
 
-def _cfg(C_: int, R: int, P: int, rays_per_cache: int, s: PathScalars) -> _cabi.TTConfig:
+def _cfg(C_: int, R: int, P: int, rays_per_cache: int, s: PathScalars, flags: int = 0) -> _cabi.TTConfig:
     return _cabi.TTConfig(C_, R, P, max(int(rays_per_cache), 1), s.radius, s.sdf_bias_radius, s.inv_std,
-                          s.cos_anneal_ratio, s.near_plane, s.far_plane, s.render_step_size)
+                          s.cos_anneal_ratio, s.near_plane, s.far_plane, s.render_step_size, flags)
+
+
+def set_impl(impl: int):
+    """1 = tcgen05 tensor-core kernels (default), 0 = SIMT fp32 reference kernels.  Both are CUDA."""
+    L = _lib()
+    _cabi.check(L, L.tt_set_impl(int(impl)), "tt_set_impl")
+
+
+def get_impl() -> int:
+    return int(_lib().tt_get_impl())
 
 
 def launch_count() -> int:
@@ -73,7 +83,7 @@ def profile_end():
     for item in buf.value.decode().split(";"):
         if item:
             name, ms = item.rsplit(":", 1)
-            recs.append((name.split("<")[0], float(ms)))
+            recs.append((name.split("<")[0].strip("( "), float(ms)))
     return recs
 
 
@@ -229,14 +239,15 @@ def render_fwd(planes, wpack, s: PathScalars, rays_o, rays_d, rays_per_cache, t_
     for k in names:
         out[k] = torch.empty((N,) if k in ("sdf", "sdf_orig", "weights", "trans") else (N, 3), device=dev,
                              dtype=torch.float32)
-    cfg = _cfg(C_, R, P, rays_per_cache, s)
+    cfg = _cfg(C_, R, P, rays_per_cache, s, 1 if extras else 0)      # TT_FLAG_ALL_FEATURES
     L = _lib()
+    scratch = torch.empty(L.tt_render_fwd_scratch_floats(n, S), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         _cabi.check(L, L.tt_render_fwd(_ptr(planes), _ptr(wpack), C.byref(cfg), _ptr(o), _ptr(d), n, _ptr(t0),
                                        _ptr(t1), stride, S, _ptr(out["acc"]),
                                        *[_ptr(out.get(k)) for k in ("sdf", "sdf_orig", "sdf_grad", "normal",
                                                                     "features", "weights", "trans")],
-                                       _stream(dev)), "tt_render_fwd")
+                                       _ptr(scratch), _stream(dev)), "tt_render_fwd")
     return out
 
 
