@@ -87,6 +87,20 @@ inline void umma(uint32_t tmem, uint32_t a_col0, uint32_t bhi, uint32_t blo, uin
             tmem_[m][c0 + 128 + n] = d;
         }
 }
+// G[128][N] (+)= At * Bt^T over 128 points; operand tiles with LBO 144 / SBO 4608 (tt_umma.cuh wg_off)
+inline void umma_ss(uint32_t d_addr, uint32_t a, uint32_t b, int N, bool acc) {
+    const int c0 = (int)(d_addr & 0xffff);
+    auto E = [&](uint32_t base, int r, int p) {
+        const uint32_t off = base + (r & 7) * 16 + (r >> 3) * 4608 + (p >> 2) * 144 + (p & 3) * 4;
+        return tf32(*(const float*)((const char*)smem_ + off));
+    };
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            float d = acc ? tmem_[m][c0 + n] : 0.f;
+            for (int p = 0; p < 128; ++p) d += E(a, m, p) * E(b, n, p);
+            tmem_[m][c0 + n] = d;
+        }
+}
 }  // namespace tt_emul
 #define threadIdx tt_emul::threadIdx_
 #define blockIdx tt_emul::blockIdx_

@@ -135,11 +135,12 @@ class Emul:
         out = dict(acc=np.zeros((n, 10), np.float32), sdf=np.zeros(N, np.float32), sdf_orig=np.zeros(N, np.float32),
                    sdf_grad=np.zeros((N, 3), np.float32), normal=np.zeros((N, 3), np.float32),
                    features=np.zeros((N, 3), np.float32), weights=np.zeros(N, np.float32),
-                   trans=np.zeros(N, np.float32))
+                   trans=np.zeros(N, np.float32), tex_masks=np.zeros((N, 2), np.uint64))
         scratch = np.zeros(self.L.tt_render_fwd_scratch_floats(n, S), np.float32)
         self.ok(self.L.tt_render_fwd(ptr(planes), ptr(wp), C.byref(cfg), ptr(o), ptr(d), n, ptr(t0), ptr(t1), S, S,
                                      *[ptr(out[k]) for k in ("acc", "sdf", "sdf_orig", "sdf_grad", "normal",
-                                                              "features", "weights", "trans")], ptr(scratch), None),
+                                                              "features", "weights", "trans")],
+                                     out["tex_masks"].ctypes.data_as(C.c_void_p), ptr(scratch), None),
                 "render_fwd")
         return out
 
@@ -156,6 +157,7 @@ class Emul:
         ga = f32(g_acc)
         self.ok(self.L.tt_render_bwd(ptr(planes), ptr(wp), C.byref(cfg), ptr(o), ptr(d), n, ptr(t0), ptr(t1), S, S,
                                      ptr(fwd["acc"]), ptr(fwd["sdf"]), ptr(fwd["sdf_grad"]), ptr(fwd["features"]),
-                                     ptr(fwd["trans"]), ptr(ga), *[ptr(x) for x in opt], rgb_scale, ptr(scratch),
+                                     ptr(fwd["trans"]), fwd["tex_masks"].ctypes.data_as(C.c_void_p), ptr(ga),
+                                     *[ptr(x) for x in opt], rgb_scale, ptr(scratch),
                                      ptr(gplanes), ptr(gw), ptr(gis), None), "render_bwd")
         return gplanes, self.split_wgrad(gw, cfg.C), float(gis[0])

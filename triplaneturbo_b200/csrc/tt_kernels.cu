@@ -2,6 +2,7 @@
 #include "../../include/triplane_b200.h"
 #include "tt_device.cuh"
 #include "tt_tc.cuh"
+#include "tt_tc_bwd.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -879,7 +880,7 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
                 }
                 if (features) {
                     if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
-                    TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, (cudaStream_t)stream, planes, wpack, *cfg, src, N, features);
+                    TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, (cudaStream_t)stream, planes, wpack, *cfg, src, N, features, (uint64_t*)nullptr);
                     if (int e = check_launch("k_tex_tc")) return e;
                 }
                 done = true;
@@ -956,7 +957,7 @@ size_t tt_render_fwd_scratch_floats(int64_t n_rays, int S) { return (size_t)n_ra
 int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
                   const float* rays_d, int64_t n_rays, const float* t_starts, const float* t_ends, int64_t t_stride,
                   int S, float* acc, float* sdf, float* sdf_orig, float* sdf_grad, float* normal, float* features,
-                  float* weights, float* trans, float* scratch, void* stream) {
+                  float* weights, float* trans, uint64_t* tex_masks, float* scratch, void* stream) {
     if (int e = check_cfg(cfg)) return e;
     if (!planes || !wpack || !acc) return fail(TT_E_ARG, "tt_render_fwd: NULL pointer%s", "");
     if (int e = check_rays("tt_render_fwd", cfg, rays_o, rays_d, n_rays, t_starts, t_ends, t_stride, S)) return e;
@@ -989,7 +990,7 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
                 if (int e = check_launch("k_weights")) return e;
                 if (!all_live) { src.index = live; src.count = count; }
                 if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
-                TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, src, N, p_feat);
+                TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, src, N, p_feat, tex_masks);
                 if (int e = check_launch("k_tex_tc")) return e;
                 TT_LAUNCH(k_accum_rgb, (unsigned)blocks, TPB, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, (const float*)p_trans, (const float*)p_feat, acc);
                 if (int e = check_launch("k_accum_rgb")) return e;
@@ -1008,10 +1009,43 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
 }
 
 static int launch_point_bwd(const float* planes, const float* wpack, const tt_config* cfg, const PtSrc& src, int64_t N,
-                            const float* gs, const float* u, const float* gf, float* gplanes, float* gw,
-                            cudaStream_t st) {
+                            const float* gs, const float* u, const float* gf, const uint64_t* tex_masks, float* gplanes,
+                            float* gw, cudaStream_t st) {
     const int64_t blocks = (N + TPB - 1) / TPB;
     if (blocks > 2147483647LL) return fail(TT_E_ARG, "too many sample points%s (%lld)", "", N);
+    if (g_impl == 1 && N < 2147483647LL) {
+        bool done = false;
+        TT_DISPATCH_C(cfg->C, {
+            {
+                const size_t smg = (size_t)BwdGeoSmem<kC>::TOTAL * 4, smt = (size_t)BwdTexSmem<kC>::TOTAL * 4;
+                if (smg <= kMaxSmem && smt <= kMaxSmem && BwdTexSmem<kC>::TMEM_OK) {
+                    TcSrc ts{};
+                    if (src.points) { ts.mode = 0; ts.points = src.points; ts.M = src.M; }
+                    else {
+                        ts.mode = 1; ts.rs = RaySrcT{src.rs.rays_o, src.rs.rays_d, src.rs.t_starts, src.rs.t_ends, src.rs.t_stride, src.rs.S};
+                        ts.rays_per_cache = src.rays_per_cache;
+                    }
+                    const int64_t tiles = (N + TC_GROUP - 1) / TC_GROUP;
+                    const unsigned grid = (unsigned)(tiles < (int64_t)num_sms() ? tiles : num_sms());
+                    if (int e = set_smem(k_bwd_geo_tc<kC>, smg)) return e;
+                    TT_LAUNCH(k_bwd_geo_tc<kC>, grid, TC_GROUP, smg, st, planes, wpack, *cfg, ts, N, gs, u, gplanes, gw);
+                    if (int e = check_launch("k_bwd_geo_tc")) return e;
+                    if (tex_masks) {
+                        if (int e = set_smem(k_bwd_tex_tc<kC>, smt)) return e;
+                        TT_LAUNCH(k_bwd_tex_tc<kC>, grid, TC_GROUP, smt, st, planes, wpack, *cfg, ts, N, gf, tex_masks, gplanes, gw);
+                        if (int e = check_launch("k_bwd_tex_tc")) return e;
+                    } else {     // no forward masks: SIMT colour backward (recomputes in fp32)
+                        const size_t sm0 = slab_bytes(kC + HID + HID + 4);
+                        if (int e = set_smem(k_bwd_tex<kC>, sm0)) return e;
+                        TT_LAUNCH(k_bwd_tex<kC>, (unsigned)blocks, TPB, sm0, st, planes, wpack, *cfg, src, N, gf, gplanes, gw);
+                        if (int e = check_launch("k_bwd_tex")) return e;
+                    }
+                    done = true;
+                }
+            }
+        });
+        if (done) return TT_OK;
+    }
     TT_DISPATCH_C(cfg->C, {
         const size_t smg = slab_bytes(kC + HID + kC + HID);
         if (int e = set_smem(k_bwd_geo<kC>, smg)) return e;
@@ -1030,9 +1064,9 @@ size_t tt_render_bwd_scratch_floats(int64_t n_rays, int S) { return (size_t)n_ra
 int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
                   const float* rays_d, int64_t n_rays, const float* t_starts, const float* t_ends, int64_t t_stride,
                   int S, const float* acc, const float* sdf, const float* sdf_grad, const float* features,
-                  const float* trans, const float* g_acc, const float* g_sdf, const float* g_sdf_grad,
-                  const float* g_normal, const float* g_features, const float* g_weights, float rgb_grad_scale,
-                  float* scratch, float* gplanes, float* gw, float* g_inv_std, void* stream) {
+                  const float* trans, const uint64_t* tex_masks, const float* g_acc, const float* g_sdf,
+                  const float* g_sdf_grad, const float* g_normal, const float* g_features, const float* g_weights,
+                  float rgb_grad_scale, float* scratch, float* gplanes, float* gw, float* g_inv_std, void* stream) {
     if (int e = check_cfg(cfg)) return e;
     if (!planes || !wpack || !acc || !sdf || !sdf_grad || !features || !trans || !g_acc || !scratch)
         return fail(TT_E_ARG, "tt_render_bwd: NULL pointer%s", "");
@@ -1049,10 +1083,10 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
     if (int e = check_launch("k_render_bwd_comp")) return e;
     if (!gplanes && !gw) return TT_OK;
     PtSrc src; src.points = nullptr; src.M = 0; src.rs = rs; src.rays_per_cache = cfg->rays_per_cache;
-    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, gplanes, gw, st);
+    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, tex_masks, gplanes, gw, st);
 }
 
-size_t tt_geometry_bwd_scratch_floats(int64_t n_points) { return (size_t)n_points * 10; }
+size_t tt_geometry_bwd_scratch_floats(int64_t n_points) { return (size_t)n_points * 14 + 16; }
 
 int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* points, int64_t M,
                        const float* g_sdf, const float* g_features, const float* g_normal, const float* g_sdf_grad,
@@ -1071,7 +1105,23 @@ int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cf
     TT_LAUNCH(k_geometry_bwd_seed, (unsigned)((N + 255) / 256), 256, 0, st, N, grad, g_sdf, g_features, g_normal, g_sdf_grad, gs, u, gf);
     if (int e = check_launch("k_geometry_bwd_seed")) return e;
     PtSrc src; src.points = points; src.M = M; src.rs = RaySrc{nullptr, nullptr, nullptr, nullptr, 0, 1}; src.rays_per_cache = 1;
-    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, gplanes, gw, st);
+    uint64_t* masks = nullptr;
+    if (g_impl == 1 && g_features && N < 2147483647LL) {      // forward ReLU masks of the colour decoder (tensor-core pass)
+        bool done = false;
+        TT_DISPATCH_C(cfg->C, {
+            const size_t smt = (size_t)TexSmem<kC>::TOTAL * 4;
+            if (smt <= kMaxSmem) {
+                masks = reinterpret_cast<uint64_t*>(scratch + ((10 * N + 3) / 4) * 4);
+                TcSrc ts{}; ts.mode = 0; ts.points = points; ts.M = M;
+                if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
+                TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, ts, N, (float*)nullptr, masks);
+                if (int e = check_launch("k_tex_tc")) return e;
+                done = true;
+            }
+        });
+        (void)done;
+    }
+    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, masks, gplanes, gw, st);
 }
 
 int tt_composite_fwd(const float* alphas, const float* values, int64_t n_rays, int S, int D, float* weights,

@@ -308,7 +308,8 @@ struct TexSmem {
 
 template <int C>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp,
-                                                         tt_config cfg, TcSrc src, int64_t N, float* feat_o) {
+                                                         tt_config cfg, TcSrc src, int64_t N, float* feat_o,
+                                                         uint64_t* masks_o) {
     TT_SHARED(smem);
     using L = TexSmem<C>;
     constexpr int SP = C + 4;
@@ -380,19 +381,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tex_tc(const float* __restric
         }
         umma_wait(u);
         umma_get_D<64>(u, d);
+        uint64_t m1 = 0, m2 = 0;
         {
             float h[64];
 #pragma unroll
-            for (int j = 0; j < 64; ++j) h[j] = fmaxf(d[j], 0.f);
+            for (int j = 0; j < 64; ++j) { m1 |= (uint64_t)(d[j] > 0.f) << j; h[j] = fmaxf(d[j], 0.f); }
             umma_layer<64, 64, 3>(u, leader, h, bW2, d);
         }
         float f[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
             const float h = fmaxf(d[j], 0.f);
+            m2 |= (uint64_t)(d[j] > 0.f) << j;
             f[0] = fmaf(h, w3[j], f[0]); f[1] = fmaf(h, w3[64 + j], f[1]); f[2] = fmaf(h, w3[128 + j], f[2]);
         }
-        if (valid) { feat_o[id * 3] = f[0]; feat_o[id * 3 + 1] = f[1]; feat_o[id * 3 + 2] = f[2]; }
+        if (valid) {
+            if (feat_o) { feat_o[id * 3] = f[0]; feat_o[id * 3 + 1] = f[1]; feat_o[id * 3 + 2] = f[2]; }
+            if (masks_o) { masks_o[id * 2] = m1; masks_o[id * 2 + 1] = m2; }     // ReLU masks for the backward
+        }
         group_sync(group);
     }
     tc_fence_before();

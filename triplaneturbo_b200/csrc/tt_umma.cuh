@@ -33,6 +33,17 @@ __device__ __forceinline__ int btile_off(int n, int k, int K) {     // float off
     return ((n & 7) * 16 + (n >> 3) * ((K >> 2) * 128) + (k >> 2) * 128 + (k & 3) * 4) >> 2;
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// round-to-nearest tf32 (single-pass operands: gradients), ties away from zero
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+// Operand tiles of the weight-gradient contractions (K = the tile's 128 points): element (row r, point p) of an
+// [R rows][128 points] K-major tile.  The 16-byte K-chunks are 144 B apart so that the 32 lanes of a warp (32
+// consecutive points, same row) write 32 different banks.
+constexpr uint32_t WG_LBO = 144, WG_SBO = 32 * 144;
+__device__ __forceinline__ int wg_off(int r, int p) {
+    return (int)(((uint32_t)(r & 7) * 16 + (uint32_t)(r >> 3) * WG_SBO + (uint32_t)(p >> 2) * WG_LBO + (uint32_t)(p & 3) * 4) >> 2);
+}
+__host__ __device__ constexpr int wg_tile_floats(int rows) { return (rows / 8) * (int)(WG_SBO / 4); }
 
 struct Umma {
     uint32_t tmem;        // TMEM address of column 0 of this group's region (lane field 0)
@@ -95,6 +106,21 @@ __device__ __forceinline__ void umma_mma(const Umma& u, const BTile& b, int K, b
         }
     }
 }
+// G[128][N] (+)= At · Btᵀ over the 128 points of a tile (both operands in shared memory, 1xTF32); one thread.
+__device__ __forceinline__ void umma_mma_ss(const Umma& u, uint32_t a_saddr, uint32_t b_saddr, int N, uint32_t d_col,
+                                            bool accumulate) {
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_tf32(N);
+    for (int ks = 0; ks < TC_GROUP / 8; ++ks) {
+        const uint64_t da = umma_desc(a_saddr + ks * 2 * WG_LBO, WG_LBO, WG_SBO);
+        const uint64_t db = umma_desc(b_saddr + ks * 2 * WG_LBO, WG_LBO, WG_SBO);
+        const uint32_t acc = (accumulate || ks > 0) ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+            ::"r"(u.tmem + d_col), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+    }
+}
 __device__ __forceinline__ void umma_commit(const Umma& u) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u.mbar) : "memory");
 }
@@ -133,6 +159,10 @@ template <int PASSES>
 __device__ __forceinline__ void umma_mma(const Umma& u, const BTile& b, int K, bool accumulate, uint32_t a_col0 = 0) {
     tt_emul::umma(u.tmem, a_col0, b.hi, b.lo, b.sbo, b.N, K, accumulate, PASSES);
 }
+__device__ __forceinline__ void umma_mma_ss(const Umma& u, uint32_t a_saddr, uint32_t b_saddr, int N, uint32_t d_col,
+                                            bool accumulate) {
+    tt_emul::umma_ss(u.tmem + d_col, a_saddr, b_saddr, N, accumulate);
+}
 __device__ __forceinline__ void umma_commit(const Umma& u) { tt_emul::mbar_arrive(u.mbar); }
 __device__ __forceinline__ void umma_wait(Umma& u) { tt_emul::mbar_wait(u.mbar, u.phase); u.phase ^= 1u; }
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) { tt_emul::tmem_st8(addr, v); }
@@ -160,13 +190,26 @@ __device__ __forceinline__ void umma_put_A(const Umma& u, const float (&x)[K], u
     tmem_wait_st();
     tc_fence_before();
 }
+// single-pass variant: only the (rounded) hi part
+template <int K>
+__device__ __forceinline__ void umma_put_A1(const Umma& u, const float (&x)[K]) {
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        uint32_t hi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hi[j] = __float_as_uint(tf32_rn(x[k0 + j]));
+        tmem_st8(u.tmem + u.lane_base + TC_COL_AHI + k0, hi);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+}
 // this thread's output row d[0..N) <- TMEM
 template <int N>
-__device__ __forceinline__ void umma_get_D(const Umma& u, float (&d)[N]) {
+__device__ __forceinline__ void umma_get_D(const Umma& u, float (&d)[N], uint32_t col = TC_COL_D) {
 #pragma unroll
     for (int n0 = 0; n0 < N; n0 += 8) {
         uint32_t v[8];
-        tmem_ld8(u.tmem + u.lane_base + TC_COL_D + n0, v);
+        tmem_ld8(u.tmem + u.lane_base + col + n0, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[n0 + j] = __uint_as_float(v[j]);
     }
@@ -176,7 +219,7 @@ __device__ __forceinline__ void umma_get_D(const Umma& u, float (&d)[N]) {
 // one full layer: put A, barrier, one thread issues + commits, everybody waits, get D
 template <int K, int N, int PASSES>
 __device__ __forceinline__ void umma_layer(Umma& u, bool leader, const float (&x)[K], const BTile& b, float (&d)[N]) {
-    umma_put_A<K>(u, x);
+    if (PASSES == 3) umma_put_A<K>(u, x); else umma_put_A1<K>(u, x);
     group_sync(u.group);
     if (leader) { umma_mma<PASSES>(u, b, K, false); umma_commit(u); }
     umma_wait(u);

@@ -239,6 +239,8 @@ def render_fwd(planes, wpack, s: PathScalars, rays_o, rays_d, rays_per_cache, t_
     for k in names:
         out[k] = torch.empty((N,) if k in ("sdf", "sdf_orig", "weights", "trans") else (N, 3), device=dev,
                              dtype=torch.float32)
+    if save_for_backward:
+        out["tex_masks"] = torch.empty((N, 2), device=dev, dtype=torch.int64)
     cfg = _cfg(C_, R, P, rays_per_cache, s, 1 if extras else 0)      # TT_FLAG_ALL_FEATURES
     L = _lib()
     scratch = torch.empty(L.tt_render_fwd_scratch_floats(n, S), device=dev, dtype=torch.float32)
@@ -246,7 +248,8 @@ def render_fwd(planes, wpack, s: PathScalars, rays_o, rays_d, rays_per_cache, t_
         _cabi.check(L, L.tt_render_fwd(_ptr(planes), _ptr(wpack), C.byref(cfg), _ptr(o), _ptr(d), n, _ptr(t0),
                                        _ptr(t1), stride, S, _ptr(out["acc"]),
                                        *[_ptr(out.get(k)) for k in ("sdf", "sdf_orig", "sdf_grad", "normal",
-                                                                    "features", "weights", "trans")],
+                                                                    "features", "weights", "trans",
+                                                                    "tex_masks")],
                                        _ptr(scratch), _stream(dev)), "tt_render_fwd")
     return out
 
@@ -270,7 +273,7 @@ def render_bwd(planes, wpack, s: PathScalars, rays_o, rays_d, rays_per_cache, t_
         _cabi.check(L, L.tt_render_bwd(_ptr(planes), _ptr(wpack), C.byref(cfg), _ptr(o), _ptr(d), n, _ptr(t0),
                                        _ptr(t1), stride, S, _ptr(saved["acc"]), _ptr(saved["sdf"]),
                                        _ptr(saved["sdf_grad"]), _ptr(saved["features"]), _ptr(saved["trans"]),
-                                       _ptr(_need(g_acc, "g_acc")), *[_ptr(g) for g in opt], float(rgb_grad_scale),
+                                       _ptr(saved.get("tex_masks")), _ptr(_need(g_acc, "g_acc")), *[_ptr(g) for g in opt], float(rgb_grad_scale),
                                        _ptr(scratch), _ptr(gplanes), _ptr(gw), _ptr(gis), _stream(dev)),
                     "tt_render_bwd")
     return gplanes, gw, gis
@@ -363,7 +366,7 @@ class RenderFunction(torch.autograd.Function):
         ctx.C = C_
         if need_grad:
             ctx.save_for_backward(planes, wpack, rays_o, rays_d, t_starts, t_ends, out["acc"], out["sdf"],
-                                  out["sdf_grad"], out["features"], out["trans"])
+                                  out["sdf_grad"], out["features"], out["trans"], out["tex_masks"])
         if not extras:
             return (out["acc"],)
         res = (out["acc"], out["sdf"].view(-1, 1), out["sdf_orig"].view(-1, 1), out["sdf_grad"], out["normal"],
@@ -374,7 +377,7 @@ class RenderFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_acc, g_sdf=None, g_sdf_orig=None, g_sdf_grad=None, g_normal=None, g_features=None,
                  g_weights=None):
-        planes, wpack, rays_o, rays_d, t0, t1, acc, sdf, sdf_grad, features, trans = ctx.saved_tensors
+        planes, wpack, rays_o, rays_d, t0, t1, acc, sdf, sdf_grad, features, trans, tex_masks = ctx.saved_tensors
         if g_sdf is not None and g_sdf_orig is not None:
             g_sdf = g_sdf + g_sdf_orig
         elif g_sdf is None:
@@ -383,7 +386,7 @@ class RenderFunction(torch.autograd.Function):
         need_w = any(ctx.needs_input_grad[1:7])
         gplanes, gw, gis = render_bwd(planes, wpack, ctx.scalars, rays_o, rays_d, ctx.rays_per_cache, t0, t1,
                                       {"acc": acc, "sdf": sdf, "sdf_grad": sdf_grad, "features": features,
-                                       "trans": trans},
+                                       "trans": trans, "tex_masks": tex_masks},
                                       g_acc, None if g_sdf is None else g_sdf.reshape(-1), g_sdf_grad, g_normal,
                                       g_features, None if g_weights is None else g_weights.reshape(-1),
                                       ctx.rgb_grad_scale, need_planes, need_w, ctx.needs_input_grad[7])
