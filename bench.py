@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="for ncu: 1 warm-up + K steps, no e2e / cpu legs (not a bench value)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
@@ -157,7 +158,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return reference_arm(args, wl, rank)
-    args.warmup = max(args.warmup, 3)
+    args.warmup = 1 if args.profile else max(args.warmup, 3)
 
     import torch.distributed as dist
     torch.cuda.set_device(local)
@@ -239,14 +240,16 @@ def main():
         return img, loss.detach().to("cpu", non_blocking=True)
     h2d = sum(t.numel() * 4 for t in (sc_h, rays_o_h, rays_d_h, c2w_h, dist_h))
     d2h = n_rays * 3 * 4 + 4
-    e2e_step(); barrier()
-    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev2[0].record()
-    for _ in range(args.steps):
-        e2e_step()
-    ev2[1].record()
-    barrier()
-    ms_e2e = ev2[0].elapsed_time(ev2[1])
+    ms_e2e = float("nan")
+    if not args.profile:
+        e2e_step(); barrier()
+        ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev2[0].record()
+        for _ in range(args.steps):
+            e2e_step()
+        ev2[1].record()
+        barrier()
+        ms_e2e = ev2[0].elapsed_time(ev2[1])
 
     times = torch.tensor([ms_total, ms_e2e], device=dev)
     if world > 1:
@@ -276,8 +279,12 @@ def main():
     kern_ms = {k: sum(v) / len(v) for k, v in by.items()}
     kern_tot = {k: sum(v) for k, v in by.items()}
     dom = max(kern_tot, key=kern_tot.get)
+    f_sdf, f_feat = fl["f_sdf"], fl["f_feat"]
+    # algorithmic dense FLOPs per ray of each kernel (per launch averages; k_geo_tc runs twice per step: proposal
+    # pass n_imp*F_sdf and fine pass S*2*F_sdf)
     flops_of = {"k_importance_sample": fl["sample"], "k_render_fwd": fl["fwd"], "k_bwd_geo": fl["bwd_geo"],
-                "k_bwd_tex": fl["bwd_tex"]}
+                "k_bwd_tex": fl["bwd_tex"], "k_geo_tc": (nimp * f_sdf + S * 2 * f_sdf) / 2.0, "k_tex_tc": S * f_feat,
+                "k_bwd_geo_tc": S * 4 * f_sdf, "k_bwd_tex_tc": S * 3 * f_feat}
     dom_flops = flops_of.get(dom, 0) * n_rays
     achieved = dom_flops / (kern_ms[dom] * 1e-3) / 1e12
     planes_bytes = P * 6 * C * R * R * 4
@@ -290,7 +297,7 @@ def main():
                 "kernels_ms": {k: round(v, 4) for k, v in kern_ms.items()}}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not args.profile:
         hw = 16
         nr, ts = time_oracle(wl, hw, 2, 1)
         cpu = {"value": nr * len(ts) / sum(ts), "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",

@@ -33,6 +33,7 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 namespace tt_emul {
@@ -42,6 +43,8 @@ inline float* smem_ = nullptr;
 inline std::barrier<>* bar_ = nullptr;
 inline std::atomic<int> or_flag_{0};
 inline std::barrier<>* gbar_[8] = {};
+inline std::barrier<>* wbar_[32] = {};
+inline uint32_t shfl_buf_[32][32];
 inline float tmem_[128][512];
 
 // ---- tcgen05 emulation (see triplaneturbo_b200/csrc/tt_umma.cuh) ------------------------------------------
@@ -108,6 +111,20 @@ inline void umma_ss(uint32_t d_addr, uint32_t a, uint32_t b, int N, bool acc) {
 #define gridDim tt_emul::gridDim_
 
 inline void __syncthreads() { tt_emul::bar_->arrive_and_wait(); }
+// warp collectives (all 32 lanes must participate)
+inline uint32_t tt_emul_shfl_u32(uint32_t v, int src_lane) {
+    const int w = (int)(threadIdx.x >> 5), l = (int)(threadIdx.x & 31);
+    tt_emul::shfl_buf_[w][l] = v;
+    tt_emul::wbar_[w]->arrive_and_wait();
+    const uint32_t r = tt_emul::shfl_buf_[w][src_lane & 31];
+    tt_emul::wbar_[w]->arrive_and_wait();
+    return r;
+}
+inline float __shfl_xor_sync(unsigned, float v, int m) {
+    uint32_t u; std::memcpy(&u, &v, 4); u = tt_emul_shfl_u32(u, (int)(threadIdx.x & 31) ^ m); std::memcpy(&v, &u, 4); return v;
+}
+inline int __shfl_sync(unsigned, int v, int lane) { return (int)tt_emul_shfl_u32((uint32_t)v, lane); }
+inline void __syncwarp() { tt_emul::wbar_[threadIdx.x >> 5]->arrive_and_wait(); }
 inline int __syncthreads_or(int pred) {
     if (pred) tt_emul::or_flag_.store(1);
     __syncthreads();
@@ -157,6 +174,11 @@ void launch(K kernel, dim3 grid, dim3 block, size_t smem_bytes, A... args) {
     smem_ = static_cast<float*>(std::align(16, smem_bytes, p, space));
     std::barrier<> bar(nthreads);
     bar_ = &bar; blockDim_ = block; gridDim_ = grid;
+    std::vector<std::unique_ptr<std::barrier<>>> warps;
+    for (unsigned w = 0; w < (nthreads + 31) / 32 && w < 32; ++w) {
+        warps.emplace_back(new std::barrier<>(std::min(32u, nthreads - w * 32)));
+        wbar_[w] = warps.back().get();
+    }
     std::vector<std::unique_ptr<std::barrier<>>> groups;
     for (unsigned g = 0; g < nthreads / 128 && g < 8; ++g) {
         groups.emplace_back(new std::barrier<>(128));

@@ -211,7 +211,8 @@ def test_other_channel_counts_against_oracle(C_):
                t_starts=t0.to(DEV), t_ends=t1.to(DEV))
     for k in ("comp_rgb", "opacity", "depth", "z_variance", "disparity", "comp_normal", "comp_normal_cam_vis",
               "weights", "sdf", "features", "normal", "sdf_grad"):
-        assert max_abs(out[k].cpu(), ref[k]) < TOL, k
+        # (this synthetic decoder has |sdf_grad| up to ~20: scale the absolute tolerance with the magnitude)
+        assert max_abs(out[k].cpu(), ref[k]) < TOL * max(1.0, float(ref[k].abs().max())), k
     g_gpu = torch.autograd.grad(loss_of(out, DEV), [sc_g] + geom.decoder_weights())
     for a, b in zip(g_gpu, g_ref):
         assert rel_err(a.cpu(), b) < GTOL

@@ -70,7 +70,9 @@ __device__ __forceinline__ void tc_point(const TcSrc& s, int64_t id, float (&x)[
 }
 
 // ---- cooperative gather: 128 points x C channels, consecutive lanes read consecutive 16-byte chunks of a texel ---
-// tap table per point: int o[NT], float w[NT] (NT = 4 * NPL), prompt-plane base offset (in floats / 4) in pbase
+// Tap table per point: int o[NT] (texel index, CLAMPED to a valid texel), float w[NT] (weight, 0 for out-of-bounds
+// taps: zeros padding), NT = 4 * NPL; pbase = prompt index.  All NT loads of an item are issued before they are
+// used, without branches, so the memory system sees NT independent 16-byte requests per lane.
 template <int C, int NPL>
 __device__ __forceinline__ void coop_gather(const float* __restrict__ planes, size_t ps, const int* tap_o,
                                             const float* tap_w, const uint32_t* pbase, int plane0, float* stage, int tg) {
@@ -80,24 +82,33 @@ __device__ __forceinline__ void coop_gather(const float* __restrict__ planes, si
         const int item = tg + TC_GROUP * j;
         const int pt = item / U, ch = item - pt * U;
         const float* base = planes + (size_t)pbase[pt] * 6 * ps + (size_t)plane0 * ps + ch * 4;
+        float4 v[NT];
+        float w[NT];
+#pragma unroll
+        for (int q = 0; q < NT; q += 4) {
+            const int4 o4 = *reinterpret_cast<const int4*>(tap_o + pt * NT + q);
+            const float4 w4 = *reinterpret_cast<const float4*>(tap_w + pt * NT + q);
+            const float* pb = base + (size_t)(q >> 2) * ps;
+            v[q] = ldg4(pb + (size_t)o4.x * C); v[q + 1] = ldg4(pb + (size_t)o4.y * C);
+            v[q + 2] = ldg4(pb + (size_t)o4.z * C); v[q + 3] = ldg4(pb + (size_t)o4.w * C);
+            w[q] = w4.x; w[q + 1] = w4.y; w[q + 2] = w4.z; w[q + 3] = w4.w;
+        }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const int o = tap_o[pt * NT + k * 4 + t];
-                if (o >= 0) {
-                    const float4 v = ldg4(base + k * ps + (size_t)o * C);
-                    const float ww = tap_w[pt * NT + k * 4 + t];
-                    s.x = fmaf(ww, v.x, s.x); s.y = fmaf(ww, v.y, s.y); s.z = fmaf(ww, v.z, s.z); s.w = fmaf(ww, v.w, s.w);
-                }
+                const float ww = w[k * 4 + t]; const float4 q = v[k * 4 + t];
+                s.x = fmaf(ww, q.x, s.x); s.y = fmaf(ww, q.y, s.y); s.z = fmaf(ww, q.z, s.z); s.w = fmaf(ww, q.w, s.w);
             }
             acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
         }
         *reinterpret_cast<float4*>(stage + pt * SP + ch * 4) = acc;
     }
 }
+// table entries of one tap: clamped offset, weight (0 when out of bounds)
+__device__ __forceinline__ int tap_off(int o) { return o < 0 ? 0 : o; }
 
 // shared-memory plan of k_geo_tc (float offsets)
 template <int C, bool NORMAL>
@@ -110,7 +121,8 @@ struct GeoSmem {
     static constexpr int GROUP0 = W3 + 64;
     // per group
     static constexpr int TAP_O = 0, TAP_W = TAP_O + 128 * 12, TAP_F = TAP_W + 128 * 12;      // ints, floats, factors
-    static constexpr int PBASE = TAP_F + (NORMAL ? 128 * 12 : 0);
+    static constexpr int TAP_V = TAP_F + (NORMAL ? 128 * 12 : 0);                              // validity (1 / 0)
+    static constexpr int PBASE = TAP_V + (NORMAL ? 128 * 12 : 0);
     static constexpr int NACC = PBASE + 128;
     static constexpr int STAGE = NACC + (NORMAL ? 128 * 6 : 0);
     static constexpr int GROUP_FLOATS = STAGE + 128 * (C + 4);
@@ -155,6 +167,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
     int* tap_o = reinterpret_cast<int*>(gs + L::TAP_O);
     float* tap_w = gs + L::TAP_W;
     float* tap_f = gs + L::TAP_F;
+    float* tap_v = gs + L::TAP_V;
     uint32_t* pbase = reinterpret_cast<uint32_t*>(gs + L::PBASE);
     float* nacc = gs + L::NACC;
     float* stage = gs + L::STAGE;
@@ -181,8 +194,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
         for (int k = 0; k < 3; ++k) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                tap_o[tg * 12 + k * 4 + t] = valid ? tp[k].o[t] : -1;
-                tap_w[tg * 12 + k * 4 + t] = valid ? tp[k].w[t] : 0.f;
+                const bool in = valid && tp[k].o[t] >= 0;
+                tap_o[tg * 12 + k * 4 + t] = in ? tp[k].o[t] : 0;
+                tap_w[tg * 12 + k * 4 + t] = in ? tp[k].w[t] : 0.f;
+                if (NORMAL) tap_v[tg * 12 + k * 4 + t] = in ? 1.f : 0.f;
             }
             if (NORMAL) {
                 tap_f[tg * 12 + k * 4 + 0] = valid ? tp[k].wx0 : 0.f; tap_f[tg * 12 + k * 4 + 1] = valid ? tp[k].wx1 : 0.f;
@@ -190,10 +205,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
             }
         }
         pbase[tg] = (uint32_t)prompt;
-        if (NORMAL) {
-#pragma unroll
-            for (int q = 0; q < 6; ++q) nacc[tg * 6 + q] = 0.f;
-        }
         group_sync(group);
         coop_gather<C, 3>(planes, ps, tap_o, tap_w, pbase, 0, stage, tg);
         group_sync(group);
@@ -240,35 +251,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
                     *reinterpret_cast<float4*>(stage + tg * SP + c) = make_float4(de[c], de[c + 1], de[c + 2], de[c + 3]);
             }
             group_sync(group);
-            {   // cooperative pass: d(de · f_k)/d(ix,iy) per plane, reduced over channel chunks with shared atomics
-                constexpr int U = C / 4;
+            {   // cooperative pass: d(de · f_k)/d(ix,iy) per plane.  SEG lanes share one point (one 16-byte channel
+                // chunk each); the partial dot products are reduced with shuffles inside the segment.
+                constexpr int U = C / 4, SEG = U > 8 ? 16 : 8, PW = 32 / SEG;
+                const int lane = tid & 31, seg = lane / SEG, ch = lane % SEG;
+                const int wpt0 = (tg >> 5) * 32;
 #pragma unroll 1
-                for (int j = 0; j < U; ++j) {
-                    const int item = tg + TC_GROUP * j;
-                    const int pt = item / U, ch = item - pt * U;
-                    const float4 dv = *reinterpret_cast<const float4*>(stage + pt * SP + ch * 4);
-                    const float* base = planes + (size_t)pbase[pt] * 6 * ps + ch * 4;
+                for (int r = 0; r < 32 / PW; ++r) {
+                    const int pt = wpt0 + r * PW + seg;
+                    float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (ch < U) {
+                        const float4 dv = *reinterpret_cast<const float4*>(stage + pt * SP + ch * 4);
+                        const float* base = planes + (size_t)pbase[pt] * 6 * ps + ch * 4;
+                        float A[12];
+                        float4 q[12];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        float A[4];
-                        bool any = false;
+                        for (int t = 0; t < 12; ++t) q[t] = ldg4(base + (size_t)(t >> 2) * ps + (size_t)tap_o[pt * 12 + t] * C);
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int o = tap_o[pt * 12 + k * 4 + t];
-                            float v = 0.f;
-                            if (o >= 0) {
-                                const float4 q = ldg4(base + k * ps + (size_t)o * C);
-                                v = dv.x * q.x + dv.y * q.y + dv.z * q.z + dv.w * q.w;
-                                any = true;
-                            }
-                            A[t] = v;
-                        }
-                        if (any) {
+                        for (int t = 0; t < 12; ++t)
+                            A[t] = (dv.x * q[t].x + dv.y * q[t].y + dv.z * q[t].z + dv.w * q[t].w) * tap_v[pt * 12 + t];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
                             const float wx0 = tap_f[pt * 12 + k * 4], wx1 = tap_f[pt * 12 + k * 4 + 1];
                             const float wy0 = tap_f[pt * 12 + k * 4 + 2], wy1 = tap_f[pt * 12 + k * 4 + 3];
-                            atomicAdd(nacc + pt * 6 + k * 2, (A[1] - A[0]) * wy0 + (A[3] - A[2]) * wy1);
-                            atomicAdd(nacc + pt * 6 + k * 2 + 1, (A[2] - A[0]) * wx0 + (A[3] - A[1]) * wx1);
+                            part[k * 2] = (A[k * 4 + 1] - A[k * 4]) * wy0 + (A[k * 4 + 3] - A[k * 4 + 2]) * wy1;
+                            part[k * 2 + 1] = (A[k * 4 + 2] - A[k * 4]) * wx0 + (A[k * 4 + 3] - A[k * 4 + 1]) * wx1;
                         }
+                    }
+#pragma unroll
+                    for (int qd = 0; qd < 6; ++qd) {
+                        float v = part[qd];
+#pragma unroll
+                        for (int off = SEG / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                        if (ch == 0) nacc[pt * 6 + qd] = v;
                     }
                 }
             }
@@ -364,7 +379,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tex_tc(const float* __restric
             Taps t;
             if (valid) t = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { tap_o[tg * 4 + q] = valid ? t.o[q] : -1; tap_w[tg * 4 + q] = valid ? t.w[q] : 0.f; }
+            for (int q = 0; q < 4; ++q) {
+                const bool in = valid && t.o[q] >= 0;
+                tap_o[tg * 4 + q] = in ? t.o[q] : 0; tap_w[tg * 4 + q] = in ? t.w[q] : 0.f;
+            }
             group_sync(group);
             coop_gather<C, 1>(planes, ps, tap_o, tap_w, pbase, 3 + k, stage, tg);
             group_sync(group);

@@ -31,7 +31,7 @@ __device__ __forceinline__ void coop_scatter(float* __restrict__ gplanes, size_t
             for (int t = 0; t < 4; ++t) {
                 const int o = tap_o[pt * NT + k * 4 + t];
                 const float ww = tap_w[pt * NT + k * 4 + t];
-                if (o >= 0 && ww != 0.f)
+                if (ww != 0.f)
                     red_add4(base + k * ps + (size_t)o * C, make_float4(v.x * ww, v.y * ww, v.z * ww, v.w * ww));
             }
     }
@@ -135,9 +135,10 @@ __global__ void __launch_bounds__(TC_GROUP, 1) k_bwd_geo_tc(const float* __restr
                                      gs * t.w[2] + (-t.wy1 * ixd + t.wx0 * iyd), gs * t.w[3] + (t.wy1 * ixd + t.wx1 * iyd)};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    tap_o[tid * 12 + k * 4 + q] = active ? t.o[q] : -1;
-                    tap_w[tid * 12 + k * 4 + q] = active ? t.w[q] : 0.f;
-                    tap_om[tid * 12 + k * 4 + q] = active ? om[q] : 0.f;
+                    const bool in = active && t.o[q] >= 0;
+                    tap_o[tid * 12 + k * 4 + q] = in ? t.o[q] : 0;
+                    tap_w[tid * 12 + k * 4 + q] = in ? t.w[q] : 0.f;
+                    tap_om[tid * 12 + k * 4 + q] = in ? om[q] : 0.f;
                 }
             }
         }
@@ -359,8 +360,9 @@ __global__ void __launch_bounds__(TC_GROUP, 1) k_bwd_tex_tc(const float* __restr
                 const Taps t = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    tap_o[k * 512 + tid * 4 + q] = active ? t.o[q] : -1;
-                    tap_w[k * 512 + tid * 4 + q] = active ? t.w[q] : 0.f;
+                    const bool in = active && t.o[q] >= 0;
+                    tap_o[k * 512 + tid * 4 + q] = in ? t.o[q] : 0;
+                    tap_w[k * 512 + tid * 4 + q] = in ? t.w[q] : 0.f;
                 }
             }
         }

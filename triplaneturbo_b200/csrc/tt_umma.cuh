@@ -142,6 +142,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(addr) : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(addr) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -167,6 +173,12 @@ __device__ __forceinline__ void umma_commit(const Umma& u) { tt_emul::mbar_arriv
 __device__ __forceinline__ void umma_wait(Umma& u) { tt_emul::mbar_wait(u.mbar, u.phase); u.phase ^= 1u; }
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) { tt_emul::tmem_st8(addr, v); }
 __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&v)[8]) { tt_emul::tmem_ld8(addr, v); }
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t* v) {
+    for (int i = 0; i < 32; i += 8) { uint32_t t[8]; for (int j = 0; j < 8; ++j) t[j] = v[i + j]; tt_emul::tmem_st8(addr + i, t); }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
+    for (int i = 0; i < 32; i += 8) { uint32_t t[8]; tt_emul::tmem_ld8(addr + i, t); for (int j = 0; j < 8; ++j) v[i + j] = t[j]; }
+}
 __device__ __forceinline__ void tmem_wait_st() {}
 __device__ __forceinline__ void tmem_wait_ld() {}
 #endif
@@ -175,8 +187,21 @@ __device__ __forceinline__ void tmem_wait_ld() {}
 // this thread's activation row x[0..K) -> TMEM (tf32 hi at A_hi, exact remainder at A_lo)
 template <int K>
 __device__ __forceinline__ void umma_put_A(const Umma& u, const float (&x)[K], uint32_t col0 = 0) {
+    constexpr int K32 = K / 32 * 32;
 #pragma unroll
-    for (int k0 = 0; k0 < K; k0 += 8) {
+    for (int k0 = 0; k0 < K32; k0 += 32) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float h = tf32_hi(x[k0 + j]);
+            hi[j] = __float_as_uint(h);
+            lo[j] = __float_as_uint(x[k0 + j] - h);
+        }
+        tmem_st32(u.tmem + u.lane_base + TC_COL_AHI + col0 + k0, hi);
+        tmem_st32(u.tmem + u.lane_base + TC_COL_ALO + col0 + k0, lo);
+    }
+#pragma unroll
+    for (int k0 = K32; k0 < K; k0 += 8) {
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -193,8 +218,16 @@ __device__ __forceinline__ void umma_put_A(const Umma& u, const float (&x)[K], u
 // single-pass variant: only the (rounded) hi part
 template <int K>
 __device__ __forceinline__ void umma_put_A1(const Umma& u, const float (&x)[K]) {
+    constexpr int K32 = K / 32 * 32;
 #pragma unroll
-    for (int k0 = 0; k0 < K; k0 += 8) {
+    for (int k0 = 0; k0 < K32; k0 += 32) {
+        uint32_t hi[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) hi[j] = __float_as_uint(tf32_rn(x[k0 + j]));
+        tmem_st32(u.tmem + u.lane_base + TC_COL_AHI + k0, hi);
+    }
+#pragma unroll
+    for (int k0 = K32; k0 < K; k0 += 8) {
         uint32_t hi[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) hi[j] = __float_as_uint(tf32_rn(x[k0 + j]));
@@ -206,8 +239,16 @@ __device__ __forceinline__ void umma_put_A1(const Umma& u, const float (&x)[K]) 
 // this thread's output row d[0..N) <- TMEM
 template <int N>
 __device__ __forceinline__ void umma_get_D(const Umma& u, float (&d)[N], uint32_t col = TC_COL_D) {
+    constexpr int N32 = N / 32 * 32;
 #pragma unroll
-    for (int n0 = 0; n0 < N; n0 += 8) {
+    for (int n0 = 0; n0 < N32; n0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(u.tmem + u.lane_base + col + n0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) d[n0 + j] = __uint_as_float(v[j]);
+    }
+#pragma unroll
+    for (int n0 = N32; n0 < N; n0 += 8) {
         uint32_t v[8];
         tmem_ld8(u.tmem + u.lane_base + col + n0, v);
 #pragma unroll
