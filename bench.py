@@ -168,6 +168,7 @@ def main():
 
     import triplaneturbo_b200 as tt  # noqa: F401
     from triplaneturbo_b200 import ops
+    from triplaneturbo_b200.parallel import allreduce_gradients
     from triplaneturbo_b200.synthetic import camera_rays, random_decoder, random_triplanes
     from tests.helpers import build_plugins
 
@@ -199,9 +200,8 @@ def main():
         loss = loss + LAMBDA_EIK * out["eikonal_sum"].sum() / (n_rays * S)
         loss = loss + LAMBDA_SPARSITY * torch.sqrt(out["opacity"] ** 2 + 0.01).mean()
         grads = torch.autograd.grad(loss, [sc] + params)
-        if world > 1:   # the one exchange of the path: decoder-weight gradients (92 KB), SURVEY 8(e)
-            flat = torch.cat([g_.reshape(-1) for g_ in grads[1:]])
-            dist.all_reduce(flat)
+        if world > 1:   # the one exchange of the path: decoder-weight gradients (92 KB) in one flat buffer, SURVEY 8(e)
+            grads = (grads[0], *allreduce_gradients(grads[1:], average=True))
         return out, loss, grads
 
     def barrier():
@@ -288,8 +288,13 @@ def main():
     dom_flops = flops_of.get(dom, 0) * n_rays
     achieved = dom_flops / (kern_ms[dom] * 1e-3) / 1e12
     planes_bytes = P * 6 * C * R * R * 4
+    traffic = None      # dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed
+    try:                # ncu --set full capture of this workload (profiles/)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(args.workload, {}).get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": kern_ms[dom], "kernel_share_of_step": kern_tot[dom] / ms_total,
                 "algorithmic_flops_per_launch": dom_flops,
                 "step_tflops": fl["step_survey"] * n_rays * args.steps / (ms_total * 1e-3) / 1e12,
