@@ -149,7 +149,9 @@ int tt_importance_sample(const float* planes, const float* wpack, const tt_confi
  * sdf_grad).
  * Per-sample outputs [n_rays*S] (all nullable; needed by tt_render_bwd: sdf, sdf_grad,
  * features, trans): sdf, sdf_orig, sdf_grad[3], normal[3], features[3], weights, trans.
- * tex_masks: [n_rays*S][2] (nullable) ReLU masks of the colour decoder, consumed by tt_render_bwd.
+ * masks: [n_rays*S][4] (nullable) 64-bit ReLU masks of the hidden layers: colour decoder [0..1], SDF decoder [2..3]
+ *   (32 B/sample), consumed by tt_render_bwd so that it recomputes neither decoder's activations pattern; when
+ *   NULL the backward runs the fp32 SIMT kernels.
  * scratch: tt_render_fwd_scratch_floats() floats (holds the per-sample state the caller did not ask for). */
 size_t tt_render_fwd_scratch_floats(int64_t n_rays, int S);
 int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
@@ -157,7 +159,7 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
                   const float* t_starts, const float* t_ends, int64_t t_stride, int S,
                   float* acc,
                   float* sdf, float* sdf_orig, float* sdf_grad, float* normal, float* features,
-                  float* weights, float* trans, uint64_t* tex_masks, float* scratch, void* stream);
+                  float* weights, float* trans, uint64_t* masks, float* scratch, void* stream);
 /* Backward.  g_acc: [n_rays][TT_ACC] gradients of the accumulators.  Per-sample upstream
  * gradients (nullable): g_sdf [N], g_sdf_grad [N][3], g_normal [N][3], g_features [N][3],
  * g_weights [N].  rgb_grad_scale multiplies the colour gradient (rgb_grad_shrink,
@@ -169,7 +171,7 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
                   const float* rays_o, const float* rays_d, int64_t n_rays,
                   const float* t_starts, const float* t_ends, int64_t t_stride, int S,
                   const float* acc, const float* sdf, const float* sdf_grad, const float* features,
-                  const float* trans, const uint64_t* tex_masks,
+                  const float* trans, const uint64_t* masks,
                   const float* g_acc, const float* g_sdf, const float* g_sdf_grad,
                   const float* g_normal, const float* g_features, const float* g_weights,
                   float rgb_grad_scale, float* scratch,

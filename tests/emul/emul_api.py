@@ -135,7 +135,7 @@ class Emul:
         out = dict(acc=np.zeros((n, 10), np.float32), sdf=np.zeros(N, np.float32), sdf_orig=np.zeros(N, np.float32),
                    sdf_grad=np.zeros((N, 3), np.float32), normal=np.zeros((N, 3), np.float32),
                    features=np.zeros((N, 3), np.float32), weights=np.zeros(N, np.float32),
-                   trans=np.zeros(N, np.float32), tex_masks=np.zeros((N, 2), np.uint64))
+                   trans=np.zeros(N, np.float32), tex_masks=np.zeros((N, 4), np.uint64))
         scratch = np.zeros(self.L.tt_render_fwd_scratch_floats(n, S), np.float32)
         self.ok(self.L.tt_render_fwd(ptr(planes), ptr(wp), C.byref(cfg), ptr(o), ptr(d), n, ptr(t0), ptr(t1), S, S,
                                      *[ptr(out[k]) for k in ("acc", "sdf", "sdf_orig", "sdf_grad", "normal",

@@ -896,10 +896,10 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
                 if (sdf || sdf_orig || want_n) {
                     if (want_n) {
                         if (int e = set_smem(k_geo_tc<kC, true>, smg_n)) return e;
-                        TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg_n, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal);
+                        TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg_n, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr);
                     } else {
                         if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
-                        TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal);
+                        TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr);
                     }
                     if (int e = check_launch("k_geo_tc")) return e;
                 }
@@ -956,7 +956,7 @@ int tt_importance_sample(const float* planes, const float* wpack, const tt_confi
                 if (int e = check_launch("k_classify")) return e;
                 src.index = list; src.count = lcount;
                 if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
-                TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, (float*)nullptr, (float*)nullptr, (float*)nullptr);
+                TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, (float*)nullptr, (float*)nullptr, (float*)nullptr, (uint64_t*)nullptr);
                 if (int e = check_launch("k_geo_tc")) return e;
                 TT_LAUNCH(k_sampler_post, (unsigned)blocks, TPB, 0, (cudaStream_t)stream, *cfg, n_rays, n_imp, n_fine, (const float*)sdf, jitter0, jitter1, cdf, t_vals);
                 if (int e = check_launch("k_sampler_post")) return e;
@@ -988,7 +988,7 @@ size_t tt_render_fwd_scratch_floats(int64_t n_rays, int S) { return (size_t)n_ra
 int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
                   const float* rays_d, int64_t n_rays, const float* t_starts, const float* t_ends, int64_t t_stride,
                   int S, float* acc, float* sdf, float* sdf_orig, float* sdf_grad, float* normal, float* features,
-                  float* weights, float* trans, uint64_t* tex_masks, float* scratch, void* stream) {
+                  float* weights, float* trans, uint64_t* masks, float* scratch, void* stream) {
     if (int e = check_cfg(cfg)) return e;
     if (!planes || !wpack || !acc) return fail(TT_E_ARG, "tt_render_fwd: NULL pointer%s", "");
     if (int e = check_rays("tt_render_fwd", cfg, rays_o, rays_d, n_rays, t_starts, t_ends, t_stride, S)) return e;
@@ -1019,7 +1019,7 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
                 if (int e = check_launch("k_classify")) return e;
                 src.index = live; src.count = count + 1;
                 if (int e = set_smem(k_geo_tc<kC, true>, smg)) return e;
-                TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, src, N, p_sdf, sdf_orig, p_grad, (float*)nullptr);
+                TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, src, N, p_sdf, sdf_orig, p_grad, (float*)nullptr, masks);
                 if (int e = check_launch("k_geo_tc")) return e;
                 src.index = nullptr; src.count = nullptr;
                 TT_LAUNCH(k_weights, (unsigned)blocks, TPB, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, acc, weights, p_trans, normal,
@@ -1027,7 +1027,7 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
                 if (int e = check_launch("k_weights")) return e;
                 if (!all_live) { src.index = live; src.count = count; }
                 if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
-                TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, src, N, p_feat, tex_masks);
+                TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, src, N, p_feat, masks);
                 if (int e = check_launch("k_tex_tc")) return e;
                 TT_LAUNCH(k_accum_rgb, (unsigned)blocks, TPB, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, (const float*)p_trans, (const float*)p_feat, acc);
                 if (int e = check_launch("k_accum_rgb")) return e;
@@ -1056,7 +1056,7 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
         TT_DISPATCH_C(cfg->C, {
             {
                 const size_t smg = (size_t)BwdGeoSmem<kC>::TOTAL * 4, smt = (size_t)BwdTexSmem<kC>::TOTAL * 4;
-                if (smg <= kMaxSmem && smt <= kMaxSmem && BwdTexSmem<kC>::TMEM_OK) {
+                if (tex_masks && smg <= kMaxSmem && smt <= kMaxSmem && BwdTexSmem<kC>::TMEM_OK) {
                     TcSrc ts{};
                     if (src.points) { ts.mode = 0; ts.points = src.points; ts.M = src.M; }
                     else {
@@ -1065,21 +1065,17 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
                     }
                     const int64_t tiles = (N + TC_GROUP - 1) / TC_GROUP;
                     const unsigned grid = (unsigned)(tiles < (int64_t)num_sms() ? tiles : num_sms());
+                    constexpr int GG = BwdGeoSmem<kC>::G;
+                    const int64_t ctas_g = (tiles + GG - 1) / GG;
+                    const unsigned grid_g = (unsigned)(ctas_g < (int64_t)num_sms() ? ctas_g : num_sms());
                     if (int e = set_smem(k_bwd_geo_tc<kC>, smg)) return e;
                     ts.index = geo_list; ts.count = geo_count;
-                    TT_LAUNCH(k_bwd_geo_tc<kC>, grid, TC_GROUP, smg, st, planes, wpack, *cfg, ts, N, gs, u, gplanes, gw);
+                    TT_LAUNCH(k_bwd_geo_tc<kC>, grid_g, GG * TC_GROUP, smg, st, planes, wpack, *cfg, ts, N, gs, u, tex_masks, gplanes, gw);
                     if (int e = check_launch("k_bwd_geo_tc")) return e;
-                    if (tex_masks) {
-                        if (int e = set_smem(k_bwd_tex_tc<kC>, smt)) return e;
-                        ts.index = tex_list; ts.count = tex_count;
-                        TT_LAUNCH(k_bwd_tex_tc<kC>, grid, TC_GROUP, smt, st, planes, wpack, *cfg, ts, N, gf, tex_masks, gplanes, gw);
-                        if (int e = check_launch("k_bwd_tex_tc")) return e;
-                    } else {     // no forward masks: SIMT colour backward (recomputes in fp32)
-                        const size_t sm0 = slab_bytes(kC + HID + HID + 4);
-                        if (int e = set_smem(k_bwd_tex<kC>, sm0)) return e;
-                        TT_LAUNCH(k_bwd_tex<kC>, (unsigned)blocks, TPB, sm0, st, planes, wpack, *cfg, src, N, gf, gplanes, gw);
-                        if (int e = check_launch("k_bwd_tex")) return e;
-                    }
+                    if (int e = set_smem(k_bwd_tex_tc<kC>, smt)) return e;
+                    ts.index = tex_list; ts.count = tex_count;
+                    TT_LAUNCH(k_bwd_tex_tc<kC>, grid, TC_GROUP, smt, st, planes, wpack, *cfg, ts, N, gf, tex_masks, gplanes, gw);
+                    if (int e = check_launch("k_bwd_tex_tc")) return e;
                     done = true;
                 }
             }
@@ -1104,7 +1100,7 @@ size_t tt_render_bwd_scratch_floats(int64_t n_rays, int S) { return (size_t)n_ra
 int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
                   const float* rays_d, int64_t n_rays, const float* t_starts, const float* t_ends, int64_t t_stride,
                   int S, const float* acc, const float* sdf, const float* sdf_grad, const float* features,
-                  const float* trans, const uint64_t* tex_masks, const float* g_acc, const float* g_sdf,
+                  const float* trans, const uint64_t* masks, const float* g_acc, const float* g_sdf,
                   const float* g_sdf_grad, const float* g_normal, const float* g_features, const float* g_weights,
                   float rgb_grad_scale, float* scratch, float* gplanes, float* gw, float* g_inv_std, void* stream) {
     if (int e = check_cfg(cfg)) return e;
@@ -1120,7 +1116,7 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
     float* gs = scratch; float* u = scratch + N; float* gf = scratch + 4 * N;
     // tensor-core family: compacted lists of the samples that can contribute (non-empty point, non-zero seed)
     int* geo_list = nullptr; int* tex_list = nullptr; int* counts = nullptr;
-    if (g_impl == 1 && N < 2147483647LL && (gplanes || gw)) {
+    if (g_impl == 1 && masks && N < 2147483647LL && (gplanes || gw)) {
         geo_list = reinterpret_cast<int*>(scratch + 7 * N); tex_list = geo_list + N; counts = tex_list + N;
         if (cudaMemsetAsync(counts, 0, 2 * sizeof(int), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
     }
@@ -1130,11 +1126,11 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
     if (int e = check_launch("k_render_bwd_comp")) return e;
     if (!gplanes && !gw) return TT_OK;
     PtSrc src; src.points = nullptr; src.M = 0; src.rs = rs; src.rays_per_cache = cfg->rays_per_cache;
-    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, tex_masks, gplanes, gw, st, geo_list, counts, tex_list,
+    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, masks, gplanes, gw, st, geo_list, counts, tex_list,
                             counts ? counts + 1 : (const int*)nullptr);
 }
 
-size_t tt_geometry_bwd_scratch_floats(int64_t n_points) { return (size_t)n_points * 14 + 16; }
+size_t tt_geometry_bwd_scratch_floats(int64_t n_points) { return (size_t)n_points * 18 + 16; }
 
 int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* points, int64_t M,
                        const float* g_sdf, const float* g_features, const float* g_normal, const float* g_sdf_grad,
@@ -1154,13 +1150,17 @@ int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cf
     if (int e = check_launch("k_geometry_bwd_seed")) return e;
     PtSrc src; src.points = points; src.M = M; src.rs = RaySrc{nullptr, nullptr, nullptr, nullptr, 0, 1}; src.rays_per_cache = 1;
     uint64_t* masks = nullptr;
-    if (g_impl == 1 && g_features && N < 2147483647LL) {      // forward ReLU masks of the colour decoder (tensor-core pass)
+    if (g_impl == 1 && N < 2147483647LL) {      // forward ReLU masks of both decoders (tensor-core passes, 3xTF32)
         bool done = false;
         TT_DISPATCH_C(cfg->C, {
-            const size_t smt = (size_t)TexSmem<kC>::TOTAL * 4;
-            if (smt <= kMaxSmem) {
+            const size_t smt = (size_t)TexSmem<kC>::TOTAL * 4, smg = (size_t)GeoSmem<kC, false>::TOTAL * 4;
+            if (smt <= kMaxSmem && smg <= kMaxSmem) {
                 masks = reinterpret_cast<uint64_t*>(scratch + ((10 * N + 3) / 4) * 4);
                 TcSrc ts{}; ts.mode = 0; ts.points = points; ts.M = M;
+                if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
+                TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, ts, N, (float*)nullptr, (float*)nullptr,
+                          (float*)nullptr, (float*)nullptr, masks);
+                if (int e = check_launch("k_geo_tc")) return e;
                 if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
                 TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, ts, N, (float*)nullptr, masks);
                 if (int e = check_launch("k_tex_tc")) return e;

@@ -192,7 +192,8 @@ struct GeoSmem {
 template <int C, bool NORMAL>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restrict__ planes, const float* __restrict__ wp,
                                                          tt_config cfg, TcSrc src, int64_t N, float* sdf_o,
-                                                         float* sdf_orig_o, float* grad_o, float* normal_o) {
+                                                         float* sdf_orig_o, float* grad_o, float* normal_o,
+                                                         uint64_t* masks_o) {
     TT_SHARED(smem);
     using L = GeoSmem<C, NORMAL>;
     constexpr int CP = L::CP, SP = C + 4;
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
         if (valid) {
             if (sdf_orig_o) sdf_orig_o[id] = s;
             if (sdf_o) sdf_o[id] = s + (nrm - cfg.sdf_bias_radius);
+            if (masks_o) { masks_o[id * 4 + 2] = m1; masks_o[id * 4 + 3] = m2; }     // ReLU masks for the backward
         }
         if (NORMAL) {
             {   // unit-seed adjoint: a2 = m2 ⊙ w3 ; a1 = m1 ⊙ (W2ᵀ a2) ; de = W1ᵀ a1
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tex_tc(const float* __restric
         }
         if (valid) {
             if (feat_o) { feat_o[id * 3] = f[0]; feat_o[id * 3 + 1] = f[1]; feat_o[id * 3 + 2] = f[2]; }
-            if (masks_o) { masks_o[id * 2] = m1; masks_o[id * 2 + 1] = m2; }     // ReLU masks for the backward
+            if (masks_o) { masks_o[id * 4] = m1; masks_o[id * 4 + 1] = m2; }     // ReLU masks for the backward
         }
         group_sync(group);
     }

@@ -240,7 +240,7 @@ def render_fwd(planes, wpack, s: PathScalars, rays_o, rays_d, rays_per_cache, t_
         out[k] = torch.empty((N,) if k in ("sdf", "sdf_orig", "weights", "trans") else (N, 3), device=dev,
                              dtype=torch.float32)
     if save_for_backward:
-        out["tex_masks"] = torch.empty((N, 2), device=dev, dtype=torch.int64)
+        out["tex_masks"] = torch.empty((N, 4), device=dev, dtype=torch.int64)
     cfg = _cfg(C_, R, P, rays_per_cache, s, 1 if extras else 0)      # TT_FLAG_ALL_FEATURES
     L = _lib()
     scratch = torch.empty(L.tt_render_fwd_scratch_floats(n, S), device=dev, dtype=torch.float32)
