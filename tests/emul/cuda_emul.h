@@ -26,6 +26,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
+#define __shared__ static          /* one block at a time: a function-local static is block-shared */
 
 struct uint3_e { unsigned x = 0, y = 0, z = 0; };
 struct dim3 {

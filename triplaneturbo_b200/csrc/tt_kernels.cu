@@ -398,10 +398,14 @@ __global__ void __launch_bounds__(TPB) k_render_bwd_comp(tt_config cfg, RaySrc r
         const float* __restrict__ g_sdf, const float* __restrict__ g_grad, const float* __restrict__ g_normal,
         const float* __restrict__ g_feat, const float* __restrict__ g_weights, float rgb_scale,
         float* __restrict__ gs_o, float* __restrict__ u_o, float* __restrict__ gf_o, float* g_inv_std,
-        int* geo_list, int* geo_count, int* tex_list, int* tex_count) {
+        int* geo_list, int* geo_count, int* tex_list, int* tex_count, uint32_t* flags) {
     const int64_t ray = (int64_t)blockIdx.x * TPB + threadIdx.x;
     float gis = 0.f;
+    int ng = 0, nt = 0;                              // entries of this ray in the two sample lists
+    const int FW = (rs.S + 15) / 16;                 // 2 flag bits per sample, 16 samples per word
     if (ray < n_rays) {
+        const float o[3] = {rs.rays_o[ray * 3], rs.rays_o[ray * 3 + 1], rs.rays_o[ray * 3 + 2]};
+        uint32_t flagw = 0;
         const float d[3] = {rs.rays_d[ray * 3], rs.rays_d[ray * 3 + 1], rs.rays_d[ray * 3 + 2]};
         const float* t0p = rs.t_starts + ray * rs.t_stride;
         const float* t1p = rs.t_ends + ray * rs.t_stride;
@@ -476,31 +480,34 @@ __global__ void __launch_bounds__(TPB) k_render_bwd_comp(tt_config cfg, RaySrc r
             }
             gs_o[si] = gsdf;
             u_o[si * 3] = u[0]; u_o[si * 3 + 1] = u[1]; u_o[si * 3 + 2] = u[2];
-        }
-    }
-    if (geo_list) {     // samples the tensor-core backward has to visit: non-empty point (an empty point depends on no
-                        // parameter) and a non-zero seed; all 32 lanes iterate together for the warp-aggregated append
-        const bool act = ray < n_rays;
-        const int64_t r = act ? ray : 0;
-        const float o[3] = {rs.rays_o[r * 3], rs.rays_o[r * 3 + 1], rs.rays_o[r * 3 + 2]};
-        const float dd[3] = {rs.rays_d[r * 3], rs.rays_d[r * 3 + 1], rs.rays_d[r * 3 + 2]};
-        for (int i = 0; i < rs.S; ++i) {
-            bool take_g = false, take_t = false;
-            if (act) {
-                const int64_t si = r * rs.S + i;
-                const bool sg = gs_o[si] != 0.f || u_o[si * 3] != 0.f || u_o[si * 3 + 1] != 0.f || u_o[si * 3 + 2] != 0.f;
+            if (geo_list) {
+                // samples the tensor-core backward has to visit: non-empty point (an empty point depends on no
+                // parameter) and a non-zero seed
+                const bool sg = gsdf != 0.f || u[0] != 0.f || u[1] != 0.f || u[2] != 0.f;
                 const bool st = gf_o[si * 3] != 0.f || gf_o[si * 3 + 1] != 0.f || gf_o[si * 3 + 2] != 0.f;
                 if (sg || st) {
-                    const float tm = __fmul_rn(__fadd_rn(rs.t_starts[r * rs.t_stride + i], rs.t_ends[r * rs.t_stride + i]), 0.5f);
-                    const float x[3] = {__fadd_rn(o[0], __fmul_rn(dd[0], tm)), __fadd_rn(o[1], __fmul_rn(dd[1], tm)),
-                                        __fadd_rn(o[2], __fmul_rn(dd[2], tm))};
-                    const bool ne = !point_empty(x, cfg.radius, cfg.R);
-                    take_g = sg && ne; take_t = st && ne;
+                    const float x[3] = {__fadd_rn(o[0], __fmul_rn(d[0], tm)), __fadd_rn(o[1], __fmul_rn(d[1], tm)),
+                                        __fadd_rn(o[2], __fmul_rn(d[2], tm))};
+                    if (!point_empty(x, cfg.radius, cfg.R)) {
+                        flagw |= ((sg ? 1u : 0u) | (st ? 2u : 0u)) << (2 * (i & 15));
+                        ng += sg ? 1 : 0; nt += st ? 1 : 0;
+                    }
+                }
+                if ((i & 15) == 0) { flags[ray * FW + (i >> 4)] = flagw; flagw = 0; }
+            }
+        }
+    }
+    if (geo_list) {     // each ray's samples land in one contiguous, ordered slice of each list (see block_reserve)
+        int at_g = tt::block_reserve<TPB>(ng, geo_count), at_t = tt::block_reserve<TPB>(nt, tex_count);
+        if (ray < n_rays && (ng | nt))
+            for (int w = 0; w < FW; ++w) {
+                uint32_t f = flags[ray * FW + w];
+                for (int b = 0; f; ++b, f >>= 2) {
+                    const int si = (int)(ray * rs.S + w * 16 + b);
+                    if (f & 1u) geo_list[at_g++] = si;
+                    if (f & 2u) tex_list[at_t++] = si;
                 }
             }
-            warp_append(take_g, (int)(r * rs.S + i), geo_list, geo_count);
-            warp_append(take_t, (int)(r * rs.S + i), tex_list, tex_count);
-        }
     }
     if (g_inv_std) {
 #ifndef TT_EMUL
@@ -1095,7 +1102,9 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
     return TT_OK;
 }
 
-size_t tt_render_bwd_scratch_floats(int64_t n_rays, int S) { return (size_t)n_rays * (size_t)S * 9 + 16; }
+size_t tt_render_bwd_scratch_floats(int64_t n_rays, int S) {
+    return (size_t)n_rays * (size_t)S * 9 + 16 + (size_t)n_rays * (size_t)((S + 15) / 16);     // seeds, lists, counters, flags
+}
 
 int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
                   const float* rays_d, int64_t n_rays, const float* t_starts, const float* t_ends, int64_t t_stride,
@@ -1122,7 +1131,7 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
     }
     TT_LAUNCH(k_render_bwd_comp, (unsigned)((n_rays + TPB - 1) / TPB), TPB, 0, st, *cfg, rs, n_rays, acc, sdf, sdf_grad, features,
         trans, g_acc, g_sdf, g_sdf_grad, g_normal, g_features, g_weights, rgb_grad_scale, gs, u, gf, g_inv_std,
-        geo_list, counts, tex_list, counts ? counts + 1 : (int*)nullptr);
+        geo_list, counts, tex_list, counts ? counts + 1 : (int*)nullptr, counts ? reinterpret_cast<uint32_t*>(counts + 16) : (uint32_t*)nullptr);
     if (int e = check_launch("k_render_bwd_comp")) return e;
     if (!gplanes && !gw) return TT_OK;
     PtSrc src; src.points = nullptr; src.M = 0; src.rs = rs; src.rays_per_cache = cfg->rays_per_cache;

@@ -102,7 +102,45 @@ __device__ __forceinline__ void warp_append(bool take, int id, int* list, int* c
 #endif
 }
 
-// one thread per point: closed-form outputs for empty points, list of the others
+// Ordered block-level reservation in a list: every thread of the block asks for n slots; slices are handed out in
+// thread order inside ONE contiguous range per block (a single atomicAdd), so that the list keeps the sample order
+// of the block (ray-major).  A warp-aggregated append (above) interleaves 32-entry chunks of every resident warp of
+// the GPU, which scatters a 128-point tile over several views and defeats L1/L2.  All threads must call.
+template <int NTHREADS>
+__device__ __forceinline__ int block_reserve(int n, int* counter) {
+    __shared__ int s_cnt[NTHREADS / 32 + 1];
+#ifndef TT_EMUL
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = n;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += v; }
+    if (lane == 31) s_cnt[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < NTHREADS / 32; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+        s_cnt[NTHREADS / 32] = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    const int r = s_cnt[NTHREADS / 32] + s_cnt[warp] + inc - n;
+    __syncthreads();
+    return r;
+#else
+    __shared__ int s_all[NTHREADS];
+    s_all[threadIdx.x] = n;
+    __syncthreads();
+    int pre = 0;
+    for (int t = 0; t < (int)threadIdx.x; ++t) pre += s_all[t];
+    if (threadIdx.x == NTHREADS - 1) s_cnt[0] = atomicAdd(counter, pre + n);
+    __syncthreads();
+    const int r = s_cnt[0] + pre;
+    __syncthreads();
+    return r;
+#endif
+}
+
+// one thread per point: closed-form outputs for empty points, list of the others (block-contiguous, in point order)
 __global__ void __launch_bounds__(256) k_classify(tt_config cfg, TcSrc src, int64_t N, float* sdf_o, float* sdf_orig_o,
                                                  float* grad_o, float* normal_o, int* list, int* count) {
     const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,7 +164,8 @@ __global__ void __launch_bounds__(256) k_classify(tt_config cfg, TcSrc src, int6
             }
         } else take = true;
     }
-    warp_append(take, (int)id, list, count);
+    const int at = block_reserve<256>(take ? 1 : 0, count);
+    if (take) list[at] = (int)id;
 }
 
 // ---- cooperative gather: 128 points x C channels, consecutive lanes read consecutive 16-byte chunks of a texel ---
@@ -136,35 +175,45 @@ __global__ void __launch_bounds__(256) k_classify(tt_config cfg, TcSrc src, int6
 template <int C, int NPL>
 __device__ __forceinline__ void coop_gather(const float* __restrict__ planes, size_t ps, const int* tap_o,
                                             const float* tap_w, const uint32_t* pbase, int plane0, float* stage, int tg) {
-    constexpr int U = C / 4, NT = 4 * NPL, SP = C + 4;
+    // JB items per batch so that 12 independent 16-byte loads are in flight per lane whatever NPL is
+    constexpr int U = C / 4, NT = 4 * NPL, SP = C + 4, JB = 3 / NPL;
 #pragma unroll 1
-    for (int j = 0; j < U; ++j) {
-        const int item = tg + TC_GROUP * j;
-        const int pt = item / U, ch = item - pt * U;
-        const float* base = planes + (size_t)pbase[pt] * 6 * ps + (size_t)plane0 * ps + ch * 4;
-        float4 v[NT];
-        float w[NT];
+    for (int j0 = 0; j0 < U; j0 += JB) {
+        float4 v[JB][NT];
+        float w[JB][NT];
+        int sto[JB];
 #pragma unroll
-        for (int q = 0; q < NT; q += 4) {
-            const int4 o4 = *reinterpret_cast<const int4*>(tap_o + pt * NT + q);
-            const float4 w4 = *reinterpret_cast<const float4*>(tap_w + pt * NT + q);
-            const float* pb = base + (size_t)(q >> 2) * ps;
-            v[q] = ldg4(pb + (size_t)o4.x * C); v[q + 1] = ldg4(pb + (size_t)o4.y * C);
-            v[q + 2] = ldg4(pb + (size_t)o4.z * C); v[q + 3] = ldg4(pb + (size_t)o4.w * C);
-            w[q] = w4.x; w[q + 1] = w4.y; w[q + 2] = w4.z; w[q + 3] = w4.w;
-        }
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < JB; ++b) {
+            const int j = j0 + b < U ? j0 + b : U - 1;          // tail batch: repeat the last item (same result)
+            const int item = tg + TC_GROUP * j;
+            const int pt = item / U, ch = item - pt * U;
+            sto[b] = pt * SP + ch * 4;
+            const float* base = planes + (size_t)pbase[pt] * 6 * ps + (size_t)plane0 * ps + ch * 4;
 #pragma unroll
-        for (int k = 0; k < NPL; ++k) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float ww = w[k * 4 + t]; const float4 q = v[k * 4 + t];
-                s.x = fmaf(ww, q.x, s.x); s.y = fmaf(ww, q.y, s.y); s.z = fmaf(ww, q.z, s.z); s.w = fmaf(ww, q.w, s.w);
+            for (int q = 0; q < NT; q += 4) {
+                const int4 o4 = *reinterpret_cast<const int4*>(tap_o + pt * NT + q);
+                const float4 w4 = *reinterpret_cast<const float4*>(tap_w + pt * NT + q);
+                const float* pb = base + (size_t)(q >> 2) * ps;
+                v[b][q] = ldg4(pb + (size_t)o4.x * C); v[b][q + 1] = ldg4(pb + (size_t)o4.y * C);
+                v[b][q + 2] = ldg4(pb + (size_t)o4.z * C); v[b][q + 3] = ldg4(pb + (size_t)o4.w * C);
+                w[b][q] = w4.x; w[b][q + 1] = w4.y; w[b][q + 2] = w4.z; w[b][q + 3] = w4.w;
             }
-            acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
         }
-        *reinterpret_cast<float4*>(stage + pt * SP + ch * 4) = acc;
+#pragma unroll
+        for (int b = 0; b < JB; ++b) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) {
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float ww = w[b][k * 4 + t]; const float4 q = v[b][k * 4 + t];
+                    s.x = fmaf(ww, q.x, s.x); s.y = fmaf(ww, q.y, s.y); s.z = fmaf(ww, q.z, s.z); s.w = fmaf(ww, q.w, s.w);
+                }
+                acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+            }
+            *reinterpret_cast<float4*>(stage + sto[b]) = acc;
+        }
     }
 }
 // table entries of one tap: clamped offset, weight (0 when out of bounds)
@@ -502,6 +551,7 @@ __global__ void __launch_bounds__(128) k_weights(tt_config cfg, RaySrcT rs, int6
     const float* t1p = rs.t_ends + r * rs.t_stride;
     const int S = rs.S;
     float T = 1.f, opac = 0.f, depth = 0.f, nsum[3] = {0.f, 0.f, 0.f}, wsum = 0.f, mean = 0.f, m2 = 0.f, eik = 0.f;
+    int n_live = 0;
     for (int i = 0; i < S; ++i) {
         bool live = false;
         const int64_t si = r * S + i;
@@ -526,9 +576,22 @@ __global__ void __launch_bounds__(128) k_weights(tt_config cfg, RaySrcT rs, int6
                                 __fadd_rn(o[2], __fmul_rn(d[2], tm))};
             live = (all_live || T > 0.f) && !point_empty(x, cfg.radius, cfg.R);   // colour of an empty point: features = 0
             if (!live && feat_zero) { feat_zero[si * 3] = 0.f; feat_zero[si * 3 + 1] = 0.f; feat_zero[si * 3 + 2] = 0.f; }
+            n_live += live ? 1 : 0;
             T *= (1.f - at.alpha);
         }
-        if (live_idx) warp_append(live, (int)si, live_idx, live_count);
+    }
+    if (live_idx) {      // second pass: the ray's live samples go to one contiguous, ordered slice of the list
+        int at = block_reserve<128>(n_live, live_count);
+        if (active_ray && n_live > 0) {
+            for (int i = 0; i < S; ++i) {
+                const int64_t si = r * S + i;
+                if (!(all_live || trans_o[si] > 0.f)) break;           // transmittance is non-increasing along the ray
+                const float tm = __fmul_rn(__fadd_rn(t0p[i], t1p[i]), 0.5f);
+                const float x[3] = {__fadd_rn(o[0], __fmul_rn(d[0], tm)), __fadd_rn(o[1], __fmul_rn(d[1], tm)),
+                                    __fadd_rn(o[2], __fmul_rn(d[2], tm))};
+                if (!point_empty(x, cfg.radius, cfg.R)) live_idx[at++] = (int)si;
+            }
+        }
     }
     if (active_ray) {
         float* a = acc_o + ray * TT_ACC;
