@@ -125,6 +125,29 @@ inline float __shfl_xor_sync(unsigned, float v, int m) {
     uint32_t u; std::memcpy(&u, &v, 4); u = tt_emul_shfl_u32(u, (int)(threadIdx.x & 31) ^ m); std::memcpy(&v, &u, 4); return v;
 }
 inline int __shfl_sync(unsigned, int v, int lane) { return (int)tt_emul_shfl_u32((uint32_t)v, lane); }
+inline float __shfl_sync(unsigned, float v, int lane) {
+    uint32_t u; std::memcpy(&u, &v, 4); u = tt_emul_shfl_u32(u, lane); std::memcpy(&v, &u, 4); return v;
+}
+inline int __shfl_up_sync(unsigned, int v, int delta) {
+    const int l = (int)(threadIdx.x & 31);
+    return (int)tt_emul_shfl_u32((uint32_t)v, l >= delta ? l - delta : l);
+}
+inline float __shfl_up_sync(unsigned, float v, int delta) {
+    const int l = (int)(threadIdx.x & 31);
+    uint32_t u; std::memcpy(&u, &v, 4); u = tt_emul_shfl_u32(u, l >= delta ? l - delta : l); std::memcpy(&v, &u, 4); return v;
+}
+inline unsigned __ballot_sync(unsigned, bool pred) {
+    const int w = (int)(threadIdx.x >> 5), l = (int)(threadIdx.x & 31);
+    tt_emul::shfl_buf_[w][l] = pred ? 1u : 0u;
+    tt_emul::wbar_[w]->arrive_and_wait();
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= (tt_emul::shfl_buf_[w][i] & 1u) << i;
+    tt_emul::wbar_[w]->arrive_and_wait();
+    return m;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i); return r; }
 inline void __syncwarp() { tt_emul::wbar_[threadIdx.x >> 5]->arrive_and_wait(); }
 inline int __syncthreads_or(int pred) {
     if (pred) tt_emul::or_flag_.store(1);

@@ -3,6 +3,7 @@
 #include "tt_device.cuh"
 #include "tt_tc.cuh"
 #include "tt_tc_bwd.cuh"
+#include "tt_rays.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -388,137 +389,7 @@ __global__ void __launch_bounds__(TPB) k_render_fwd(const float* __restrict__ pl
     a[9] = eik;
 }
 
-// =====================================================================================================
-// backward, stage 1: compositing + alpha + normalisation, one thread per ray, reverse order.
-// Writes per-sample seeds for stage 2: gs (d/d sdf), u[3] (d/d sdf_grad), gf[3] (d/d features).
-// =====================================================================================================
-__global__ void __launch_bounds__(TPB) k_render_bwd_comp(tt_config cfg, RaySrc rs, int64_t n_rays,
-        const float* __restrict__ acc, const float* __restrict__ sdf, const float* __restrict__ grad,
-        const float* __restrict__ feat, const float* __restrict__ trans, const float* __restrict__ g_acc,
-        const float* __restrict__ g_sdf, const float* __restrict__ g_grad, const float* __restrict__ g_normal,
-        const float* __restrict__ g_feat, const float* __restrict__ g_weights, float rgb_scale,
-        float* __restrict__ gs_o, float* __restrict__ u_o, float* __restrict__ gf_o, float* g_inv_std,
-        int* geo_list, int* geo_count, int* tex_list, int* tex_count, uint32_t* flags) {
-    const int64_t ray = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    float gis = 0.f;
-    int ng = 0, nt = 0;                              // entries of this ray in the two sample lists
-    const int FW = (rs.S + 15) / 16;                 // 2 flag bits per sample, 16 samples per word
-    if (ray < n_rays) {
-        const float o[3] = {rs.rays_o[ray * 3], rs.rays_o[ray * 3 + 1], rs.rays_o[ray * 3 + 2]};
-        uint32_t flagw = 0;
-        const float d[3] = {rs.rays_d[ray * 3], rs.rays_d[ray * 3 + 1], rs.rays_d[ray * 3 + 2]};
-        const float* t0p = rs.t_starts + ray * rs.t_stride;
-        const float* t1p = rs.t_ends + ray * rs.t_stride;
-        const int S = rs.S;
-        const float* ga = g_acc + ray * TT_ACC;
-        const float opac = acc[ray * TT_ACC], D = acc[ray * TT_ACC + 1];
-        const float gE = ga[9];
-        const float gO = ga[0], gZ = ga[5];
-        const float gD = ga[1] + gZ * (-2.f) * D * (1.f - opac);    // z_variance depends on depth[ray]
-        const float gC[3] = {ga[2], ga[3], ga[4]}, gN[3] = {ga[6], ga[7], ga[8]};
-        const float car = cfg.cos_anneal_ratio, inv_std = cfg.inv_std;
-        float Rh = 0.f;     // Σ_{j>i} gw_j α_j Π_{i<k<j} (1-α_k)
-        for (int i = S - 1; i >= 0; --i) {
-            const int64_t si = ray * S + i;
-            const float t0 = t0p[i], t1 = t1p[i];
-            const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f), dt = __fsub_rn(t1, t0);
-            const float s = sdf[si];
-            const float g[3] = {grad[si * 3], grad[si * 3 + 1], grad[si * 3 + 2]};
-            const float f[3] = {feat[si * 3], feat[si * 3 + 1], feat[si * 3 + 2]};
-            const float T = trans[si];
-            float n[3], len; normalize3(g, n, len);
-            const AlphaTerms at = neus_alpha(s, n, d, dt, inv_std, car);
-            const float w = T * at.alpha;
-            float c[3], sg[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { sg[a] = sigmoidf(f[a]); c[a] = sg[a] * 1.002f - 0.001f; }
-            float gw = gO + gD * tm + gC[0] * c[0] + gC[1] * c[1] + gC[2] * c[2] + gN[0] * n[0] + gN[1] * n[1] +
-                       gN[2] * n[2] + gZ * (tm - D) * (tm - D);
-            if (g_weights) gw += g_weights[si];
-            const float galpha = T * (gw - Rh);
-            Rh = gw * at.alpha + (1.f - at.alpha) * Rh;
-            // colour
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                float v = w * gC[a] * rgb_scale * 1.002f * sg[a] * (1.f - sg[a]);
-                if (g_feat) v += g_feat[si * 3 + a];
-                gf_o[si * 3 + a] = v;
-            }
-            // alpha -> sdf, normal
-            float gn[3] = {w * gN[0], w * gN[1], w * gN[2]};
-            if (g_normal) { gn[0] += g_normal[si * 3]; gn[1] += g_normal[si * 3 + 1]; gn[2] += g_normal[si * 3 + 2]; }
-            float gsdf = g_sdf ? g_sdf[si] : 0.f;
-            if (at.alpha_raw >= 0.f && at.alpha_raw <= 1.f && galpha != 0.f) {
-                const float den = at.prev_cdf + 1e-5f;
-                const float gnum = galpha / den, gden = -galpha * at.alpha_raw / den;
-                const float gpc = gnum + gden, gnc = -gnum;
-                const float dp = at.prev_cdf * (1.f - at.prev_cdf), dn = at.next_cdf * (1.f - at.next_cdf);
-                const float gsp = gpc * dp * inv_std, gsn = gnc * dn * inv_std;
-                gis += gpc * dp * at.s_prev + gnc * dn * at.s_next;
-                gsdf += gsp + gsn;
-                const float giter = (gsn - gsp) * dt * 0.5f;
-                const float dct = 0.5f * (1.f - car) * ((-at.true_cos * 0.5f + 0.5f) > 0.f ? 1.f : 0.f) +
-                                  car * ((-at.true_cos) > 0.f ? 1.f : 0.f);
-                const float gtc = giter * dct;
-                gn[0] += gtc * d[0]; gn[1] += gtc * d[1]; gn[2] += gtc * d[2];
-            }
-            // n = g / max(|g|, eps)
-            float u[3] = {0.f, 0.f, 0.f};
-            if (len > 1e-12f) {
-                const float dotv = n[0] * gn[0] + n[1] * gn[1] + n[2] * gn[2];
-                const float il = 1.f / len;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) u[a] = (gn[a] - n[a] * dotv) * il;
-            } else {
-#pragma unroll
-                for (int a = 0; a < 3; ++a) u[a] = gn[a] * 1e12f;
-            }
-            if (g_grad) { u[0] += g_grad[si * 3]; u[1] += g_grad[si * 3 + 1]; u[2] += g_grad[si * 3 + 2]; }
-            if (gE != 0.f && len > 0.f) {                       // d (|g|-1)^2 / d g = 2 (|g|-1) g / |g|
-                const float ce = gE * 2.f * (len - 1.f) / len;
-                u[0] += ce * g[0]; u[1] += ce * g[1]; u[2] += ce * g[2];
-            }
-            gs_o[si] = gsdf;
-            u_o[si * 3] = u[0]; u_o[si * 3 + 1] = u[1]; u_o[si * 3 + 2] = u[2];
-            if (geo_list) {
-                // samples the tensor-core backward has to visit: non-empty point (an empty point depends on no
-                // parameter) and a non-zero seed
-                const bool sg = gsdf != 0.f || u[0] != 0.f || u[1] != 0.f || u[2] != 0.f;
-                const bool st = gf_o[si * 3] != 0.f || gf_o[si * 3 + 1] != 0.f || gf_o[si * 3 + 2] != 0.f;
-                if (sg || st) {
-                    const float x[3] = {__fadd_rn(o[0], __fmul_rn(d[0], tm)), __fadd_rn(o[1], __fmul_rn(d[1], tm)),
-                                        __fadd_rn(o[2], __fmul_rn(d[2], tm))};
-                    if (!point_empty(x, cfg.radius, cfg.R)) {
-                        flagw |= ((sg ? 1u : 0u) | (st ? 2u : 0u)) << (2 * (i & 15));
-                        ng += sg ? 1 : 0; nt += st ? 1 : 0;
-                    }
-                }
-                if ((i & 15) == 0) { flags[ray * FW + (i >> 4)] = flagw; flagw = 0; }
-            }
-        }
-    }
-    if (geo_list) {     // each ray's samples land in one contiguous, ordered slice of each list (see block_reserve)
-        int at_g = tt::block_reserve<TPB>(ng, geo_count), at_t = tt::block_reserve<TPB>(nt, tex_count);
-        if (ray < n_rays && (ng | nt))
-            for (int w = 0; w < FW; ++w) {
-                uint32_t f = flags[ray * FW + w];
-                for (int b = 0; f; ++b, f >>= 2) {
-                    const int si = (int)(ray * rs.S + w * 16 + b);
-                    if (f & 1u) geo_list[at_g++] = si;
-                    if (f & 2u) tex_list[at_t++] = si;
-                }
-            }
-    }
-    if (g_inv_std) {
-#ifndef TT_EMUL
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) gis += __shfl_xor_sync(0xffffffffu, gis, off);
-        if ((threadIdx.x & 31) == 0 && gis != 0.f) atomicAdd(g_inv_std, gis);
-#else
-        if (gis != 0.f) atomicAdd(g_inv_std, gis);
-#endif
-    }
-}
+// backward, stage 1 (compositing + alpha + normalisation -> per-sample seeds): k_render_bwd_comp in tt_rays.cuh
 
 // seeds for the stand-alone geometry backward: gs = g_sdf, u = g_sdf_grad + d normalize, gf = g_features
 __global__ void k_geometry_bwd_seed(int64_t N, const float* __restrict__ grad /*sdf_grad, needed iff g_normal*/,
@@ -1029,14 +900,14 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
                 TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, src, N, p_sdf, sdf_orig, p_grad, (float*)nullptr, masks);
                 if (int e = check_launch("k_geo_tc")) return e;
                 src.index = nullptr; src.count = nullptr;
-                TT_LAUNCH(k_weights, (unsigned)blocks, TPB, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, acc, weights, p_trans, normal,
+                TT_LAUNCH(k_weights, (unsigned)((n_rays + RAY_WARPS - 1) / RAY_WARPS), RAY_WARPS * 32, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, acc, weights, p_trans, normal,
                           all_live ? (float*)nullptr : p_feat, all_live ? (int*)nullptr : live, count, all_live);
                 if (int e = check_launch("k_weights")) return e;
                 if (!all_live) { src.index = live; src.count = count; }
                 if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
                 TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, src, N, p_feat, masks);
                 if (int e = check_launch("k_tex_tc")) return e;
-                TT_LAUNCH(k_accum_rgb, (unsigned)blocks, TPB, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, (const float*)p_trans, (const float*)p_feat, acc);
+                TT_LAUNCH(k_accum_rgb, (unsigned)((n_rays + RAY_WARPS - 1) / RAY_WARPS), RAY_WARPS * 32, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, (const float*)p_trans, (const float*)p_feat, acc);
                 if (int e = check_launch("k_accum_rgb")) return e;
                 done = true;
             }
@@ -1103,7 +974,7 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
 }
 
 size_t tt_render_bwd_scratch_floats(int64_t n_rays, int S) {
-    return (size_t)n_rays * (size_t)S * 9 + 16 + (size_t)n_rays * (size_t)((S + 15) / 16);     // seeds, lists, counters, flags
+    return (size_t)n_rays * (size_t)S * 9 + 16 + (size_t)n_rays * 2 * (size_t)ray_chunks(S);     // seeds, lists, counters, flags
 }
 
 int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
@@ -1121,6 +992,7 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
     if (n_rays <= 0) return TT_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const RaySrc rs{rays_o, rays_d, t_starts, t_ends, t_stride, S};
+    const RaySrcT rst{rays_o, rays_d, t_starts, t_ends, t_stride, S};
     const int64_t N = n_rays * S;
     float* gs = scratch; float* u = scratch + N; float* gf = scratch + 4 * N;
     // tensor-core family: compacted lists of the samples that can contribute (non-empty point, non-zero seed)
@@ -1129,7 +1001,7 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
         geo_list = reinterpret_cast<int*>(scratch + 7 * N); tex_list = geo_list + N; counts = tex_list + N;
         if (cudaMemsetAsync(counts, 0, 2 * sizeof(int), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
     }
-    TT_LAUNCH(k_render_bwd_comp, (unsigned)((n_rays + TPB - 1) / TPB), TPB, 0, st, *cfg, rs, n_rays, acc, sdf, sdf_grad, features,
+    TT_LAUNCH(k_render_bwd_comp, (unsigned)((n_rays + RAY_WARPS - 1) / RAY_WARPS), RAY_WARPS * 32, 0, st, *cfg, rst, n_rays, acc, sdf, sdf_grad, features,
         trans, g_acc, g_sdf, g_sdf_grad, g_normal, g_features, g_weights, rgb_grad_scale, gs, u, gf, g_inv_std,
         geo_list, counts, tex_list, counts ? counts + 1 : (int*)nullptr, counts ? reinterpret_cast<uint32_t*>(counts + 16) : (uint32_t*)nullptr);
     if (int e = check_launch("k_render_bwd_comp")) return e;

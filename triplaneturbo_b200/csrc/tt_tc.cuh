@@ -535,97 +535,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tex_tc(const float* __restric
     if (warp == 0) tmem_dealloc_warp(*tmem_slot, 512);
 }
 
-// ---- per-ray NeuS alpha + compositing of everything that does not need colour --------------------------------------
-// Reads per-sample sdf / sdf_grad, writes trans (and weights, normal if requested), the non-colour accumulators and
-// the list of live samples (transmittance > 0), whose colour is the only one that can reach the image or a gradient.
-__global__ void __launch_bounds__(128) k_weights(tt_config cfg, RaySrcT rs, int64_t n_rays, const float* __restrict__ sdf,
-                                                const float* __restrict__ grad, float* __restrict__ acc_o,
-                                                float* weights_o, float* trans_o, float* normal_o, float* feat_zero,
-                                                int* live_idx, int* live_count, int all_live) {
-    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active_ray = ray < n_rays;
-    const int64_t r = active_ray ? ray : 0;
-    const float d[3] = {rs.rays_d[r * 3], rs.rays_d[r * 3 + 1], rs.rays_d[r * 3 + 2]};
-    const float o[3] = {rs.rays_o[r * 3], rs.rays_o[r * 3 + 1], rs.rays_o[r * 3 + 2]};
-    const float* t0p = rs.t_starts + r * rs.t_stride;
-    const float* t1p = rs.t_ends + r * rs.t_stride;
-    const int S = rs.S;
-    float T = 1.f, opac = 0.f, depth = 0.f, nsum[3] = {0.f, 0.f, 0.f}, wsum = 0.f, mean = 0.f, m2 = 0.f, eik = 0.f;
-    int n_live = 0;
-    for (int i = 0; i < S; ++i) {
-        bool live = false;
-        const int64_t si = r * S + i;
-        if (active_ray) {
-            const float t0 = t0p[i], t1 = t1p[i];
-            const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f), dt = __fsub_rn(t1, t0);
-            const float g[3] = {grad[si * 3], grad[si * 3 + 1], grad[si * 3 + 2]};
-            float n[3], len; normalize3(g, n, len);
-            const AlphaTerms at = neus_alpha(sdf[si], n, d, dt, cfg.inv_std, cfg.cos_anneal_ratio);
-            eik += (len - 1.f) * (len - 1.f);
-            const float w = T * at.alpha;
-            opac += w; depth = fmaf(w, tm, depth);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) nsum[a] = fmaf(w, n[a], nsum[a]);
-            const float wn = wsum + w;
-            if (wn > 0.f) { const float dl = tm - mean; mean += (w / wn) * dl; m2 += w * dl * (tm - mean); }
-            wsum = wn;
-            if (weights_o) weights_o[si] = w;
-            if (trans_o) trans_o[si] = T;
-            if (normal_o) { normal_o[si * 3] = n[0]; normal_o[si * 3 + 1] = n[1]; normal_o[si * 3 + 2] = n[2]; }
-            const float x[3] = {__fadd_rn(o[0], __fmul_rn(d[0], tm)), __fadd_rn(o[1], __fmul_rn(d[1], tm)),
-                                __fadd_rn(o[2], __fmul_rn(d[2], tm))};
-            live = (all_live || T > 0.f) && !point_empty(x, cfg.radius, cfg.R);   // colour of an empty point: features = 0
-            if (!live && feat_zero) { feat_zero[si * 3] = 0.f; feat_zero[si * 3 + 1] = 0.f; feat_zero[si * 3 + 2] = 0.f; }
-            n_live += live ? 1 : 0;
-            T *= (1.f - at.alpha);
-        }
-    }
-    if (live_idx) {      // second pass: the ray's live samples go to one contiguous, ordered slice of the list
-        int at = block_reserve<128>(n_live, live_count);
-        if (active_ray && n_live > 0) {
-            for (int i = 0; i < S; ++i) {
-                const int64_t si = r * S + i;
-                if (!(all_live || trans_o[si] > 0.f)) break;           // transmittance is non-increasing along the ray
-                const float tm = __fmul_rn(__fadd_rn(t0p[i], t1p[i]), 0.5f);
-                const float x[3] = {__fadd_rn(o[0], __fmul_rn(d[0], tm)), __fadd_rn(o[1], __fmul_rn(d[1], tm)),
-                                    __fadd_rn(o[2], __fmul_rn(d[2], tm))};
-                if (!point_empty(x, cfg.radius, cfg.R)) live_idx[at++] = (int)si;
-            }
-        }
-    }
-    if (active_ray) {
-        float* a = acc_o + ray * TT_ACC;
-        a[0] = opac; a[1] = depth; a[2] = 0.f; a[3] = 0.f; a[4] = 0.f;
-        a[5] = m2 + wsum * (mean - depth) * (mean - depth);
-        a[6] = nsum[0]; a[7] = nsum[1]; a[8] = nsum[2]; a[9] = eik;
-    }
-}
-
-// rgb accumulator: Σ_i (T_i alpha_i) sigmoid_mipnerf(f_i); weights are recomputed from trans (w = T - T_next)
-__global__ void __launch_bounds__(128) k_accum_rgb(tt_config cfg, RaySrcT rs, int64_t n_rays, const float* __restrict__ sdf,
-                                                  const float* __restrict__ grad, const float* __restrict__ trans,
-                                                  const float* __restrict__ feat, float* __restrict__ acc_o) {
-    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ray >= n_rays) return;
-    const float d[3] = {rs.rays_d[ray * 3], rs.rays_d[ray * 3 + 1], rs.rays_d[ray * 3 + 2]};
-    const float* t0p = rs.t_starts + ray * rs.t_stride;
-    const float* t1p = rs.t_ends + ray * rs.t_stride;
-    const int S = rs.S;
-    float rgb[3] = {0.f, 0.f, 0.f};
-    for (int i = 0; i < S; ++i) {
-        const int64_t si = ray * S + i;
-        const float T = trans[si];
-        if (T <= 0.f) break;                     // transmittance is non-increasing along the ray
-        const float dt = __fsub_rn(t1p[i], t0p[i]);
-        const float g[3] = {grad[si * 3], grad[si * 3 + 1], grad[si * 3 + 2]};
-        float n[3], len; normalize3(g, n, len);
-        const float w = T * neus_alpha(sdf[si], n, d, dt, cfg.inv_std, cfg.cos_anneal_ratio).alpha;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) rgb[a] = fmaf(w, sigmoid_mipnerf(feat[si * 3 + a]), rgb[a]);
-    }
-    acc_o[ray * TT_ACC + 2] = rgb[0]; acc_o[ray * TT_ACC + 3] = rgb[1]; acc_o[ray * TT_ACC + 4] = rgb[2];
-}
-
 // importance sampler, stage 2: proposal sdf [n_rays][n_imp] -> density -> cdf -> inverse-CDF draws -> sorted edges
 __global__ void __launch_bounds__(128) k_sampler_post(tt_config cfg, int64_t n_rays, int n_imp, int n_fine,
                                                      const float* __restrict__ sdf, const float* __restrict__ jit0,
