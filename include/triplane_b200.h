@@ -116,9 +116,9 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
 /* Backward of tt_geometry_fwd w.r.t. planes and decoder weights (second order through the
  * analytic normal; replaces autograd + grid_sample_gradfix/gridsample_cuda.cu:27-210).
  * Upstream gradients (nullable): g_sdf [N] (sum of the grads of sdf and sdf_orig),
- * g_features [N][3], g_normal [N][3], g_sdf_grad [N][3].  scratch: tt_geometry_bwd_scratch_floats(P*M)
- * floats.  gplanes/gw are ACCUMULATED into. */
-size_t tt_geometry_bwd_scratch_floats(int64_t n_points);
+ * g_features [N][3], g_normal [N][3], g_sdf_grad [N][3].  scratch: tt_geometry_bwd_scratch_floats(cfg, P*M)
+ * floats (per-point seeds, masks and the hidden-gradient planes [P][3][R*R][64] of the colour backward).  gplanes/gw are ACCUMULATED into. */
+size_t tt_geometry_bwd_scratch_floats(const tt_config* cfg, int64_t n_points);
 int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cfg,
                     const float* points, int64_t M,
                     const float* g_sdf, const float* g_features, const float* g_normal,
@@ -163,10 +163,11 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
 /* Backward.  g_acc: [n_rays][TT_ACC] gradients of the accumulators.  Per-sample upstream
  * gradients (nullable): g_sdf [N], g_sdf_grad [N][3], g_normal [N][3], g_features [N][3],
  * g_weights [N].  rgb_grad_scale multiplies the colour gradient (rgb_grad_shrink,
- * …sdf_volume_renderer.py:397-400).  scratch: tt_render_bwd_scratch_floats() floats.
+ * …sdf_volume_renderer.py:397-400).  scratch: tt_render_bwd_scratch_floats(cfg, n_rays, S) floats
+ * (per-sample seeds, sample lists, hidden-gradient planes [P][3][R*R][64] of the colour backward).
  * gplanes [P][6][R][R][C] and gw (tt_wgrad_floats) are ACCUMULATED into; g_inv_std (1 float,
  * nullable) likewise. */
-size_t tt_render_bwd_scratch_floats(int64_t n_rays, int S);
+size_t tt_render_bwd_scratch_floats(const tt_config* cfg, int64_t n_rays, int S);
 int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
                   const float* rays_o, const float* rays_d, int64_t n_rays,
                   const float* t_starts, const float* t_ends, int64_t t_stride, int S,

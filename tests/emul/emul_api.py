@@ -102,7 +102,7 @@ class Emul:
         pts = f32(points)
         M = pts.shape[1]
         N = cfg.P * M
-        scratch = np.zeros(self.L.tt_geometry_bwd_scratch_floats(N), np.float32)
+        scratch = np.zeros(self.L.tt_geometry_bwd_scratch_floats(C.byref(cfg), N), np.float32)
         gplanes = aligned_zeros(planes.shape)
         gw = aligned_zeros(self.L.tt_wgrad_floats(cfg.C))
         a = [None if x is None else f32(x) for x in (g_sdf, g_features, g_normal, g_sdf_grad)]
@@ -149,7 +149,7 @@ class Emul:
         o, d = f32(rays_o).reshape(-1, 3), f32(rays_d).reshape(-1, 3)
         t0, t1 = f32(t_starts), f32(t_ends)
         n, S = t0.shape
-        scratch = np.zeros(self.L.tt_render_bwd_scratch_floats(n, S), np.float32)
+        scratch = np.zeros(self.L.tt_render_bwd_scratch_floats(C.byref(cfg), n, S), np.float32)
         gplanes = aligned_zeros(planes.shape)
         gw = aligned_zeros(self.L.tt_wgrad_floats(cfg.C))
         gis = np.zeros(1, np.float32)

@@ -43,7 +43,11 @@ def test_size_queries_and_offsets(lib):
         assert list(off) == [0, 64 * C_, 64 * C_ + 4096, 64 * C_ + 4160, 256 * C_ + 4160, 256 * C_ + 8256]
         assert lib.tt_wpack_floats(C_) > lib.tt_wgrad_floats(C_)
     assert lib.tt_wpack_floats(12) == 0
-    assert lib.tt_render_bwd_scratch_floats(10, 7) >= 490      # 7 seed floats per sample + compaction lists
+    cfg = _cabi.TTConfig(8, 16, 2, 5, 1.0, 0.5, 100.0, 1.0, 0.1, 4.0, 0.05, 0)
+    # 7 seed floats per sample + compaction lists + hidden-gradient planes [P][3][R*R][64]
+    assert lib.tt_render_bwd_scratch_floats(C.byref(cfg), 10, 7) >= 630 + 2 * 3 * 256 * 64
+    assert lib.tt_render_bwd_scratch_floats(None, 10, 7) >= 630
+    assert lib.tt_geometry_bwd_scratch_floats(C.byref(cfg), 10) >= 180 + 2 * 3 * 256 * 64
     assert lib.tt_sample_scratch_floats(10, 16) >= 340
 
 

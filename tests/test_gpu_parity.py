@@ -214,8 +214,9 @@ def test_other_channel_counts_against_oracle(C_):
         # (this synthetic decoder has |sdf_grad| up to ~20: scale the absolute tolerance with the magnitude)
         assert max_abs(out[k].cpu(), ref[k]) < TOL * max(1.0, float(ref[k].abs().max())), k
     g_gpu = torch.autograd.grad(loss_of(out, DEV), [sc_g] + geom.decoder_weights())
-    for a, b in zip(g_gpu, g_ref):
-        assert rel_err(a.cpu(), b) < GTOL
+    names = ["space_cache", "sdf.0", "sdf.1", "sdf.2", "feature.0", "feature.1", "feature.2"]
+    errs = {n: rel_err(a.cpu(), b) for n, a, b in zip(names, g_gpu, g_ref)}
+    assert all(e < GTOL for e in errs.values()), errs
 
 
 def test_full_size_properties():

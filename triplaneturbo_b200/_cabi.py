@@ -42,13 +42,13 @@ SIGNATURES = {
     "tt_repack_planes": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp]),
     "tt_repack_planes_bwd": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, fp, fp]),
     "tt_geometry_fwd": (C.c_int, [fp, fp, _cfgp, fp, i64, C.c_int] + [fp] * 6 + [fp]),
-    "tt_geometry_bwd_scratch_floats": (C.c_size_t, [i64]),
+    "tt_geometry_bwd_scratch_floats": (C.c_size_t, [_cfgp, i64]),
     "tt_geometry_bwd": (C.c_int, [fp, fp, _cfgp, fp, i64] + [fp] * 4 + [fp, fp, fp, fp]),
     "tt_sample_scratch_floats": (C.c_size_t, [i64, C.c_int]),
     "tt_importance_sample": (C.c_int, [fp, fp, _cfgp, fp, fp, i64, C.c_int, C.c_int, fp, fp, fp, fp, fp]),
     "tt_render_fwd_scratch_floats": (C.c_size_t, [i64, C.c_int]),
     "tt_render_fwd": (C.c_int, [fp, fp, _cfgp, fp, fp, i64, fp, fp, i64, C.c_int] + [fp] * 8 + [fp, fp, fp]),
-    "tt_render_bwd_scratch_floats": (C.c_size_t, [i64, C.c_int]),
+    "tt_render_bwd_scratch_floats": (C.c_size_t, [_cfgp, i64, C.c_int]),
     "tt_render_bwd": (C.c_int, [fp, fp, _cfgp, fp, fp, i64, fp, fp, i64, C.c_int] + [fp] * 6 + [fp] * 6 +
                       [C.c_float, fp, fp, fp, fp, fp]),
     "tt_composite_fwd": (C.c_int, [fp, fp, i64, C.c_int, C.c_int, fp, fp, fp, fp]),

@@ -923,10 +923,15 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
     return check_launch("tt_render_fwd");
 }
 
+static size_t hid_floats(const tt_config* cfg) {      // hidden-gradient planes of the colour backward, [P][3][R*R][64]
+    return cfg ? (size_t)cfg->P * 3 * (size_t)cfg->R * (size_t)cfg->R * 64 : 0;
+}
+static size_t round4(size_t n) { return (n + 3) / 4 * 4; }
+
 static int launch_point_bwd(const float* planes, const float* wpack, const tt_config* cfg, const PtSrc& src, int64_t N,
                             const float* gs, const float* u, const float* gf, const uint64_t* tex_masks, float* gplanes,
-                            float* gw, cudaStream_t st, const int* geo_list = nullptr, const int* geo_count = nullptr,
-                            const int* tex_list = nullptr, const int* tex_count = nullptr) {
+                            float* gw, float* hid, cudaStream_t st, const int* geo_list = nullptr,
+                            const int* geo_count = nullptr, const int* tex_list = nullptr, const int* tex_count = nullptr) {
     const int64_t blocks = (N + TPB - 1) / TPB;
     if (blocks > 2147483647LL) return fail(TT_E_ARG, "too many sample points%s (%lld)", "", N);
     if (g_impl == 1 && N < 2147483647LL) {
@@ -934,7 +939,7 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
         TT_DISPATCH_C(cfg->C, {
             {
                 const size_t smg = (size_t)BwdGeoSmem<kC>::TOTAL * 4, smt = (size_t)BwdTexSmem<kC>::TOTAL * 4;
-                if (tex_masks && smg <= kMaxSmem && smt <= kMaxSmem && BwdTexSmem<kC>::TMEM_OK) {
+                if (tex_masks && hid && smg <= kMaxSmem && smt <= kMaxSmem) {
                     TcSrc ts{};
                     if (src.points) { ts.mode = 0; ts.points = src.points; ts.M = src.M; }
                     else {
@@ -950,10 +955,29 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
                     ts.index = geo_list; ts.count = geo_count;
                     TT_LAUNCH(k_bwd_geo_tc<kC>, grid_g, GG * TC_GROUP, smg, st, planes, wpack, *cfg, ts, N, gs, u, tex_masks, gplanes, gw);
                     if (int e = check_launch("k_bwd_geo_tc")) return e;
+                    // colour branch: per-sample kernel scatters the 64-wide hidden gradient, then two dense products
+                    constexpr int GT = BwdTexSmem<kC>::G;
+                    const int64_t ctas_t = (tiles + GT - 1) / GT;
+                    const unsigned grid_t = (unsigned)(ctas_t < (int64_t)num_sms() ? ctas_t : num_sms());
+                    if (cudaMemsetAsync(hid, 0, hid_floats(cfg) * sizeof(float), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
                     if (int e = set_smem(k_bwd_tex_tc<kC>, smt)) return e;
                     ts.index = tex_list; ts.count = tex_count;
-                    TT_LAUNCH(k_bwd_tex_tc<kC>, grid, TC_GROUP, smt, st, planes, wpack, *cfg, ts, N, gf, tex_masks, gplanes, gw);
+                    TT_LAUNCH(k_bwd_tex_tc<kC>, grid_t, GT * TC_GROUP, smt, st, planes, wpack, *cfg, ts, N, gf, tex_masks, hid, gw);
                     if (int e = check_launch("k_bwd_tex_tc")) return e;
+                    if (gplanes) {
+                        const size_t smh = (size_t)64 * kC * 4;
+                        const int64_t items = (int64_t)cfg->P * cfg->R * cfg->R * (kC / 4);
+                        const int64_t nb = (items + 255) / 256;
+                        TT_LAUNCH(k_hid_planes<kC>, dim3((unsigned)(nb < 8 * num_sms() ? nb : 8 * num_sms()), 3), 256, smh, st, (const float*)hid, wpack, cfg->P, cfg->R, gplanes);
+                        if (int e = check_launch("k_hid_planes")) return e;
+                    }
+                    if (gw) {
+                        const size_t smw = (size_t)(64 * 65 + 64 * (kC + 1)) * 4;
+                        const int64_t slabs = (int64_t)cfg->P * (((int64_t)cfg->R * cfg->R + 63) / 64);
+                        TT_LAUNCH(k_hid_wgrad<kC>, dim3((unsigned)(slabs < num_sms() ? slabs : num_sms()), 3), 256, smw, st, (const float*)hid, planes, cfg->P, cfg->R, gw);
+                        if (int e = check_launch("k_hid_wgrad")) return e;
+                    }
+                    (void)grid;
                     done = true;
                 }
             }
@@ -973,8 +997,9 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
     return TT_OK;
 }
 
-size_t tt_render_bwd_scratch_floats(int64_t n_rays, int S) {
-    return (size_t)n_rays * (size_t)S * 9 + 16 + (size_t)n_rays * 2 * (size_t)ray_chunks(S);     // seeds, lists, counters, flags
+size_t tt_render_bwd_scratch_floats(const tt_config* cfg, int64_t n_rays, int S) {
+    // seeds, lists, counters, flags | hidden-gradient planes
+    return round4((size_t)n_rays * (size_t)S * 9 + 16 + (size_t)n_rays * 2 * (size_t)ray_chunks(S)) + hid_floats(cfg);
 }
 
 int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
@@ -997,7 +1022,9 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
     float* gs = scratch; float* u = scratch + N; float* gf = scratch + 4 * N;
     // tensor-core family: compacted lists of the samples that can contribute (non-empty point, non-zero seed)
     int* geo_list = nullptr; int* tex_list = nullptr; int* counts = nullptr;
-    if (g_impl == 1 && masks && N < 2147483647LL && (gplanes || gw)) {
+    bool fwd_tc = false;     // did tt_render_fwd take the tensor-core path (and write the ReLU masks)?  Same test as there.
+    TT_DISPATCH_C(cfg->C, { fwd_tc = (size_t)GeoSmem<kC, true>::TOTAL * 4 <= kMaxSmem && (size_t)TexSmem<kC>::TOTAL * 4 <= kMaxSmem; });
+    if (g_impl == 1 && fwd_tc && masks && N < 2147483647LL && (gplanes || gw)) {
         geo_list = reinterpret_cast<int*>(scratch + 7 * N); tex_list = geo_list + N; counts = tex_list + N;
         if (cudaMemsetAsync(counts, 0, 2 * sizeof(int), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
     }
@@ -1007,11 +1034,13 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
     if (int e = check_launch("k_render_bwd_comp")) return e;
     if (!gplanes && !gw) return TT_OK;
     PtSrc src; src.points = nullptr; src.M = 0; src.rs = rs; src.rays_per_cache = cfg->rays_per_cache;
-    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, masks, gplanes, gw, st, geo_list, counts, tex_list,
+    float* hid = scratch + round4((size_t)N * 9 + 16 + (size_t)n_rays * 2 * (size_t)ray_chunks(S));
+    if (!geo_list) masks = nullptr;      // the forward ran the SIMT kernels (no masks were written): SIMT backward
+    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, masks, gplanes, gw, hid, st, geo_list, counts, tex_list,
                             counts ? counts + 1 : (const int*)nullptr);
 }
 
-size_t tt_geometry_bwd_scratch_floats(int64_t n_points) { return (size_t)n_points * 18 + 16; }
+size_t tt_geometry_bwd_scratch_floats(const tt_config* cfg, int64_t n_points) { return round4((size_t)n_points * 18 + 16) + hid_floats(cfg); }
 
 int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* points, int64_t M,
                        const float* g_sdf, const float* g_features, const float* g_normal, const float* g_sdf_grad,
@@ -1050,7 +1079,7 @@ int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cf
         });
         (void)done;
     }
-    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, masks, gplanes, gw, st);
+    return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, masks, gplanes, gw, scratch + round4((size_t)N * 18 + 16), st);
 }
 
 int tt_composite_fwd(const float* alphas, const float* values, int64_t n_rays, int S, int D, float* weights,

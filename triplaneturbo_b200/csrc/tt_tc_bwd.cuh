@@ -244,210 +244,224 @@ k_bwd_geo_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
 }
 
 // ================================================================================================ colour branch
+// First-layer gradients through a HIDDEN-GRADIENT PLANE.  With g1 = dL/d(pre-activation of layer 1) [64] per sample,
+// e_k = Σ_t w_t · texel_k(o_t) the sampled encoding of texture plane k and W1_k the [64][C] block of the first layer:
+//     dL/dtexel_k(o) = Σ_{samples, taps hitting o} w_t · W1_kᵀ g1      =  (H_k W1_k)(o)
+//     dL/dW1_k        = Σ_samples g1 ⊗ e_k                              =  H_kᵀ · planes_k
+// where H_k(o)[64] = Σ w_t · g1 is the scatter of the 64-wide hidden gradient.  So the per-sample work of the first layer
+// is ONE scatter (no second gather of e_k, no W1ᵀ layer, no per-tile dW1 contraction), and the two products above are
+// dense [R²x64]·[64xC] / [64xR²]·[R²xC] contractions done once per backward by k_hid_planes / k_hid_wgrad (fp32 FMA).
+// Per tile: gather e_k (3 planes) -> h1 = relu(Σ W1_k e_k) -> z2 = W2 h1 (single-pass TF32, masks from the forward),
+// g2 = m2 ⊙ W3ᵀ gf, dW2 += g2 h1ᵀ (TMEM accumulator), g1 = m1 ⊙ W2ᵀ g2, dW3 += gf h2ᵀ (SIMT from the h2 operand tile),
+// scatter g1·w into H.  G independent 128-thread groups per CTA; TMEM per group: A [0,64) dW2 [64,128) D [128,192).
 template <int C>
 struct BwdTexSmem {
-    static constexpr int CP = (C + 15) / 16 * 16;
-    static constexpr int AT = 0, BT = AT + wg_tile_floats(72);                  // rows 0-63: g_h; rows 64-71: gf (3 used)
-    static constexpr int W1H = BT + wg_tile_floats(64), W2H = W1H + 3 * 64 * C, W2TH = W2H + 4096, W1TH = W2TH + 4096;
-    static constexpr int W3 = W1TH + 3 * CP * 64;
-    static constexpr int TAP_O = W3 + 192, TAP_W = TAP_O + 128 * 12, PBASE = TAP_W + 128 * 12, STAGE = PBASE + 128;
-    static constexpr int TOTAL = STAGE + 128 * (C + 4) + 16;
-    // TMEM columns: A [0,64), D1 [64,128), D0 [128,192), dW2 [192,256), dW3 [256,320), dW1 3 x CP from 320,
-    // de_k: k=0 at D0, k=1 at D1, k=2 at 320 + 3 CP
-    static constexpr uint32_t COL_D1 = 64, COL_GW2 = 192, COL_GW3 = 256, COL_GW1 = 320, COL_DE2 = 320 + 3 * CP;
-    static constexpr bool TMEM_OK = 320 + 4 * CP <= 512;     // otherwise the host falls back to the SIMT kernels
+    static constexpr int HS = 68;                                               // row stride of the staged g1 [128][64]
+    static constexpr int W1H = 0, W2H = W1H + 3 * 64 * C, W2TH = W2H + 4096, W3 = W2TH + 4096;
+    static constexpr int GROUP0 = W3 + 192;
+    static constexpr int AT = 0, BT = AT + wg_tile_floats(64), STAGE = BT;      // STAGE aliases the B tile
+    static constexpr int TAP_O = BT + wg_tile_floats(64), TAP_W = TAP_O + 128 * 4, PBASE = TAP_W + 128 * 4;
+    static constexpr int GF = PBASE + 128;
+    static constexpr int GROUP_FLOATS = GF + 3 * 128;
+    static constexpr int G = (GROUP0 + 2 * GROUP_FLOATS + 16) * 4 <= 227 * 1024 ? 2 : 1;
+    static constexpr int TOTAL = GROUP0 + G * GROUP_FLOATS + 16;
+    static constexpr uint32_t COL_GW2 = 64;
+    static_assert(128 * (C + 4) <= wg_tile_floats(64) && 128 * HS <= wg_tile_floats(64), "stage must fit in the B tile");
 };
 
+// scatter the staged 64-wide rows into the hidden-gradient planes hid[P][3][R*R][64]
+__device__ __forceinline__ void coop_scatter_hid(float* __restrict__ hid, size_t hs, const int* tap_o, const float* tap_w,
+                                                 const uint32_t* pbase, int k, const float* stage, int stride, int tg) {
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) {
+        const int item = tg + TC_GROUP * j;
+        const int pt = item >> 4, ch = item & 15;
+        const float4 v = *reinterpret_cast<const float4*>(stage + pt * stride + ch * 4);
+        float* base = hid + ((size_t)pbase[pt] * 3 + k) * hs + ch * 4;
+        const int4 o4 = *reinterpret_cast<const int4*>(tap_o + pt * 4);
+        const float4 w4 = *reinterpret_cast<const float4*>(tap_w + pt * 4);
+        if (w4.x != 0.f) red_add4(base + (size_t)o4.x * 64, make_float4(v.x * w4.x, v.y * w4.x, v.z * w4.x, v.w * w4.x));
+        if (w4.y != 0.f) red_add4(base + (size_t)o4.y * 64, make_float4(v.x * w4.y, v.y * w4.y, v.z * w4.y, v.w * w4.y));
+        if (w4.z != 0.f) red_add4(base + (size_t)o4.z * 64, make_float4(v.x * w4.z, v.y * w4.z, v.z * w4.z, v.w * w4.z));
+        if (w4.w != 0.f) red_add4(base + (size_t)o4.w * 64, make_float4(v.x * w4.w, v.y * w4.w, v.z * w4.w, v.w * w4.w));
+    }
+}
+
 template <int C>
-__global__ void __launch_bounds__(TC_GROUP, 1) k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp,
-                                                           tt_config cfg, TcSrc src, int64_t N,
-                                                           const float* __restrict__ gf_i,
-                                                           const uint64_t* __restrict__ masks,
-                                                           float* __restrict__ gplanes, float* __restrict__ gw) {
+__global__ void __launch_bounds__(BwdTexSmem<C>::G * TC_GROUP, 1)
+k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_config cfg, TcSrc src, int64_t N,
+             const float* __restrict__ gf_i, const uint64_t* __restrict__ masks, float* __restrict__ hid,
+             float* __restrict__ gw) {
     TT_SHARED(smem);
     using L = BwdTexSmem<C>;
-    constexpr int CP = L::CP, SP = C + 4;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    constexpr int SP = C + 4, HS = L::HS, G = L::G, NT = G * TC_GROUP;
+    const int tid = threadIdx.x, group = tid / TC_GROUP, tg = tid % TC_GROUP, warp = tid >> 5;
     const WOff wo = woff(C);
     const GOff go = goff(C);
-    for (int k = 0; k < 3; ++k) {
-        for (int i = tid; i < 64 * C; i += TC_GROUP) {          // W1f plane tiles [64][C] (forward, single pass)
-            const int n = i / C, kk = i % C;
-            smem[L::W1H + k * 64 * C + btile_off(n, kk, C)] = tf32_rn(__ldg(wp + wo.w1f + n * 3 * C + k * C + kk));
-        }
-        for (int i = tid; i < CP * 64; i += TC_GROUP) {         // W1f_kᵀ tiles [CP][64]
-            const int n = i / 64, kk = i % 64;
-            smem[L::W1TH + k * CP * 64 + btile_off(n, kk, 64)] = n < C ? tf32_rn(__ldg(wp + wo.w1f + kk * 3 * C + k * C + n)) : 0.f;
-        }
+    for (int i = tid; i < 3 * 64 * C; i += NT) {              // W1f as three [64][C] K-major tiles (single pass)
+        const int k = i / (64 * C), r = i - k * 64 * C, n = r / C, kk = r % C;
+        smem[L::W1H + k * 64 * C + btile_off(n, kk, C)] = tf32_rn(__ldg(wp + wo.w1f + n * 3 * C + k * C + kk));
     }
-    for (int i = tid; i < 4096; i += TC_GROUP) {
+    for (int i = tid; i < 4096; i += NT) {
         const int n = i / 64, k = i % 64;
         smem[L::W2H + btile_off(n, k, 64)] = tf32_rn(__ldg(wp + wo.w2f + n * 64 + k));
         smem[L::W2TH + btile_off(n, k, 64)] = tf32_rn(__ldg(wp + wo.w2f + k * 64 + n));
     }
-    for (int i = tid; i < wg_tile_floats(72) + wg_tile_floats(64); i += TC_GROUP) smem[L::AT + i] = 0.f;
-    for (int i = tid; i < 192; i += TC_GROUP) smem[L::W3 + i] = __ldg(wp + wo.w3f + i);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L::STAGE + 128 * (C + 4));
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
-    if (tid == 0) mbar_init(mbar);
-    if (warp == 0) tmem_alloc_warp(tmem_slot, 512);
+    for (int i = tid; i < 192; i += NT) smem[L::W3 + i] = __ldg(wp + wo.w3f + i);
+    float* gsm = smem + L::GROUP0 + group * L::GROUP_FLOATS;
+    for (int i = tg; i < 2 * wg_tile_floats(64); i += TC_GROUP) gsm[L::AT + i] = 0.f;
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::GROUP0 + G * L::GROUP_FLOATS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + G);
+    if (tid == 0) for (int g = 0; g < G; ++g) mbar_init(mbars + g);
+    if (warp == 0) tmem_alloc_warp(tmem_slot, G * TC_COLS_PER_GROUP);
     async_proxy_fence();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     Umma u;
-    u.tmem = *tmem_slot; u.lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    u.mbar = smem_u32(mbar); u.phase = 0; u.group = 0;
-    const bool leader = tid == 0;
-    BTile bW1[3], bW1T[3];
-    for (int k = 0; k < 3; ++k) {
-        bW1[k] = btile_make(smem + L::W1H + k * 64 * C, smem + L::W1H + k * 64 * C, 64, C);
-        bW1T[k] = btile_make(smem + L::W1TH + k * CP * 64, smem + L::W1TH + k * CP * 64, CP, 64);
-    }
+    u.tmem = *tmem_slot + (uint32_t)group * TC_COLS_PER_GROUP;
+    u.lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    u.mbar = smem_u32(mbars + group); u.phase = 0; u.group = group;
+    const bool leader = tg == 0;
+    BTile bW1[3];
+    for (int k = 0; k < 3; ++k) bW1[k] = btile_make(smem + L::W1H + k * 64 * C, smem + L::W1H + k * 64 * C, 64, C);
     const BTile bW2 = btile_make(smem + L::W2H, smem + L::W2H, 64, 64);
     const BTile bW2T = btile_make(smem + L::W2TH, smem + L::W2TH, 64, 64);
-    float* At = smem + L::AT; float* Bt = smem + L::BT;
+    float* At = gsm + L::AT; float* Bt = gsm + L::BT;
     const uint32_t at_addr = smem_u32(At), bt_addr = smem_u32(Bt);
-    const uint32_t at_gf_addr = at_addr + 8 * WG_SBO;            // row group 8: rows 64..71 hold gf
-    int* tap_o = reinterpret_cast<int*>(smem + L::TAP_O);
-    float* tap_w = smem + L::TAP_W;
-    uint32_t* pbase = reinterpret_cast<uint32_t*>(smem + L::PBASE);
-    float* stage = smem + L::STAGE;
+    int* tap_o = reinterpret_cast<int*>(gsm + L::TAP_O);
+    float* tap_w = gsm + L::TAP_W;
+    uint32_t* pbase = reinterpret_cast<uint32_t*>(gsm + L::PBASE);
+    float* gfs = gsm + L::GF;
+    float* stage = gsm + L::STAGE;
     const float* w3 = smem + L::W3;
-    const size_t ps = (size_t)cfg.R * cfg.R * C;
+    const size_t ps = (size_t)cfg.R * cfg.R * C, hs = (size_t)cfg.R * cfg.R * 64;
     const int64_t n_live = src.count ? (int64_t)*src.count : N;
     const int64_t n_tiles = (n_live + TC_GROUP - 1) / TC_GROUP;
     bool any_tile = false;
+    float dw3[3] = {0.f, 0.f, 0.f};            // dW3[c][j] partial: j = tg & 63 over the points of half tg >> 6
+    const int j3 = tg & 63, half3 = tg >> 6;
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t slot = tile * TC_GROUP + tid;
+    for (int64_t tile = (int64_t)blockIdx.x * G + group; tile < n_tiles; tile += (int64_t)gridDim.x * G) {
+        const int64_t slot = tile * TC_GROUP + tg;
         const bool valid = slot < n_live;
         const int64_t id = valid ? (src.index ? (int64_t)src.index[slot] : slot) : 0;
         float gf[3] = {0.f, 0.f, 0.f};
         if (valid) { gf[0] = gf_i[id * 3]; gf[1] = gf_i[id * 3 + 1]; gf[2] = gf_i[id * 3 + 2]; }
         const bool active = valid && (gf[0] != 0.f || gf[1] != 0.f || gf[2] != 0.f);
-        if (!__syncthreads_or(active)) continue;        // nothing to do in this tile
+        // the ReLU masks are the forward's (3xTF32) masks: a single-pass recompute may flip units near zero
+        const uint64_t m1 = active ? masks[id * 4] : 0ull, m2 = active ? masks[id * 4 + 1] : 0ull;
         int prompt = 0;
+        float p[3];
         {
-            float x[3] = {0.f, 0.f, 0.f}, p[3];
+            float x[3] = {0.f, 0.f, 0.f};
             if (active) tc_point(src, id, x, prompt);
 #pragma unroll
             for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const Taps t = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const bool in = active && t.o[q] >= 0;
-                    tap_o[k * 512 + tid * 4 + q] = in ? t.o[q] : 0;
-                    tap_w[k * 512 + tid * 4 + q] = in ? t.w[q] : 0.f;
-                }
-            }
         }
-        pbase[tid] = (uint32_t)prompt;
+        pbase[tg] = (uint32_t)prompt;
+        gfs[tg] = gf[0]; gfs[128 + tg] = gf[1]; gfs[256 + tg] = gf[2];
         float d[64];
-        // ---- recompute (single pass): h1 = relu(Σ_k W1f_k e_k), h2 = relu(W2f h1) ----------------------------------
+        // ---- recompute (single pass): z1 = Σ_k W1f_k e_k, z2 = W2f relu(z1) -----------------------------------------
 #pragma unroll 1
         for (int k = 0; k < 3; ++k) {
-            group_sync(0);
-            coop_gather<C, 1>(planes, ps, tap_o + k * 512, tap_w + k * 512, pbase, 3 + k, stage, tid);
-            group_sync(0);
+            {
+                const Taps t = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
+                int4 o4; float4 w4;
+                o4.x = (active && t.o[0] >= 0) ? t.o[0] : 0; w4.x = (active && t.o[0] >= 0) ? t.w[0] : 0.f;
+                o4.y = (active && t.o[1] >= 0) ? t.o[1] : 0; w4.y = (active && t.o[1] >= 0) ? t.w[1] : 0.f;
+                o4.z = (active && t.o[2] >= 0) ? t.o[2] : 0; w4.z = (active && t.o[2] >= 0) ? t.w[2] : 0.f;
+                o4.w = (active && t.o[3] >= 0) ? t.o[3] : 0; w4.w = (active && t.o[3] >= 0) ? t.w[3] : 0.f;
+                *reinterpret_cast<int4*>(tap_o + tg * 4) = o4;
+                *reinterpret_cast<float4*>(tap_w + tg * 4) = w4;
+            }
+            group_sync(group);
+            coop_gather<C, 1>(planes, ps, tap_o, tap_w, pbase, 3 + k, stage, tg);
+            group_sync(group);
             float e[C];
 #pragma unroll
             for (int c = 0; c < C; c += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(stage + tid * SP + c);
+                const float4 v = *reinterpret_cast<const float4*>(stage + tg * SP + c);
                 e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
             }
-            if (k > 0) umma_wait(u);
+            if (k > 0) umma_wait(u);          // previous chunk's MMAs are done reading A
             umma_put_A1<C>(u, e);
-            group_sync(0);
+            group_sync(group);
             if (leader) { umma_mma<1>(u, bW1[k], C, k > 0); umma_commit(u); }
         }
         umma_wait(u);
         umma_get_D<64>(u, d);
-        // the ReLU masks are the forward's (3xTF32) masks: a single-pass recompute may flip units near zero
-        const uint64_t m1 = active ? masks[id * 4] : 0ull, m2 = active ? masks[id * 4 + 1] : 0ull;
+        // ---- g2 = m2 ⊙ W3ᵀ gf needs only the masks: dW2 += g2 h1ᵀ is issued together with z2 = W2 h1 ------------------
         {
             float h[64];
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
-                const bool on = (m1 >> j) & 1ull;
-                h[j] = on ? d[j] : 0.f;
-                Bt[wg_off(j, tid)] = tf32_rn(h[j]);                                   // h1 -> B tile of dW2
+                h[j] = ((m1 >> j) & 1ull) ? d[j] : 0.f;
+                Bt[wg_off(j, tg)] = tf32_rn(h[j]);                                   // h1 -> B tile of dW2
+                const float v = gf[0] * w3[j] + gf[1] * w3[64 + j] + gf[2] * w3[128 + j];
+                At[wg_off(j, tg)] = ((m2 >> j) & 1ull) ? tf32_rn(v) : 0.f;           // g2 -> A tile of dW2
             }
-            umma_layer<64, 64, 1>(u, leader, h, bW2, d);                              // pre-activations stay in D0
+            umma_put_A1<64>(u, h);
+            async_proxy_fence();
+            group_sync(group);
+            if (leader) {
+                if (gw) umma_mma_ss(u, at_addr, bt_addr, 64, L::COL_GW2, any_tile);
+                umma_mma<1>(u, bW2, 64, false);
+                umma_commit(u);
+            }
+            umma_wait(u);
+            umma_get_D<64>(u, d);                                                    // z2
         }
-        // ---- g_h2 = m2 ⊙ W3ᵀ gf ; dW2 += g_h2 h1ᵀ ; g_h1 = m1 ⊙ W2ᵀ g_h2 (output to D1 so that D0 keeps h2) ---------
+        // ---- dW3 += gf h2ᵀ from the h2 operand tile (SIMT: 3 x 64 outputs, 64 points per thread) ---------------------
+        if (gw) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) Bt[wg_off(j, tg)] = ((m2 >> j) & 1ull) ? d[j] : 0.f;      // h2
+        }
+        // ---- g1 = m1 ⊙ W2ᵀ g2 ---------------------------------------------------------------------------------------
+        float g1[64];
         {
             float g2[64];
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
                 const float v = gf[0] * w3[j] + gf[1] * w3[64 + j] + gf[2] * w3[128 + j];
                 g2[j] = ((m2 >> j) & 1ull) ? v : 0.f;
-                At[wg_off(j, tid)] = tf32_rn(g2[j]);
             }
+            umma_layer<64, 64, 1>(u, leader, g2, bW2T, g1);      // (its group_sync also publishes the h2 tile)
+        }
+        if (gw) {
+#pragma unroll 4
+            for (int q = 0; q < 16; ++q) {
+                const int p0 = half3 * 64 + q * 4;
+                const float4 hv = *reinterpret_cast<const float4*>(Bt + wg_off(j3, p0));
 #pragma unroll
-            for (int c = 0; c < 3; ++c) At[wg_off(64 + c, tid)] = tf32_rn(gf[c]);
-            umma_put_A1<64>(u, g2);
-            async_proxy_fence();
-            group_sync(0);
-            if (leader) {
-                if (gw) umma_mma_ss(u, at_addr, bt_addr, 64, L::COL_GW2, any_tile);
-                umma_mma<1>(u, bW2T, 64, false);
-                umma_commit(u);
+                for (int c = 0; c < 3; ++c) {
+                    const float4 gv = *reinterpret_cast<const float4*>(gfs + c * 128 + p0);
+                    dw3[c] = fmaf(gv.x, hv.x, fmaf(gv.y, hv.y, fmaf(gv.z, hv.z, fmaf(gv.w, hv.w, dw3[c]))));
+                }
             }
-            umma_wait(u);
         }
-        float gh1[64];                       // (`d` still holds the layer-2 pre-activations: h2 = relu(d))
-        umma_get_D<64>(u, gh1);
+        group_sync(group);                     // the B tile becomes the stage of g1
 #pragma unroll
-        for (int j = 0; j < 64; ++j) gh1[j] = ((m1 >> j) & 1ull) ? gh1[j] : 0.f;
-        // ---- dW3 += gf h2ᵀ (A rows 64..66), then the three data gradients de_k = W1f_kᵀ g_h1 ---------------------------
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            Bt[wg_off(j, tid)] = ((m2 >> j) & 1ull) ? tf32_rn(d[j]) : 0.f;             // h2
-            At[wg_off(j, tid)] = tf32_rn(gh1[j]);                                      // g_h1 -> A tile of dW1
-        }
-        umma_put_A1<64>(u, gh1);
-        async_proxy_fence();
-        group_sync(0);
-        if (leader) {
-            if (gw) umma_mma_ss(u, at_gf_addr, bt_addr, 64, L::COL_GW3, any_tile);
-            umma_commit(u);
-        }
-        umma_wait(u);
+        for (int j = 0; j < 64; j += 4)
+            *reinterpret_cast<float4*>(stage + tg * HS + j) =
+                make_float4(((m1 >> j) & 1ull) ? g1[j] : 0.f, ((m1 >> (j + 1)) & 1ull) ? g1[j + 1] : 0.f,
+                            ((m1 >> (j + 2)) & 1ull) ? g1[j + 2] : 0.f, ((m1 >> (j + 3)) & 1ull) ? g1[j + 3] : 0.f);
+        // ---- scatter g1 · w into the hidden-gradient planes ----------------------------------------------------------
 #pragma unroll 1
         for (int k = 0; k < 3; ++k) {
-            // de_k = W1f_kᵀ g_h1 (A = g_h1 still in TMEM), and dW1_k += g_h1 e_kᵀ with e_k re-gathered
-            coop_gather<C, 1>(planes, ps, tap_o + k * 512, tap_w + k * 512, pbase, 3 + k, stage, tid);
-            group_sync(0);
             {
-                float e[C];
-#pragma unroll
-                for (int c = 0; c < C; c += 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(stage + tid * SP + c);
-                    e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
-                }
-#pragma unroll
-                for (int c = 0; c < C; ++c) Bt[wg_off(c, tid)] = tf32_rn(e[c]);
+                const Taps t = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
+                int4 o4; float4 w4;
+                o4.x = (active && t.o[0] >= 0) ? t.o[0] : 0; w4.x = (active && t.o[0] >= 0) ? t.w[0] : 0.f;
+                o4.y = (active && t.o[1] >= 0) ? t.o[1] : 0; w4.y = (active && t.o[1] >= 0) ? t.w[1] : 0.f;
+                o4.z = (active && t.o[2] >= 0) ? t.o[2] : 0; w4.z = (active && t.o[2] >= 0) ? t.w[2] : 0.f;
+                o4.w = (active && t.o[3] >= 0) ? t.o[3] : 0; w4.w = (active && t.o[3] >= 0) ? t.w[3] : 0.f;
+                *reinterpret_cast<int4*>(tap_o + tg * 4) = o4;
+                *reinterpret_cast<float4*>(tap_w + tg * 4) = w4;
             }
-            async_proxy_fence();
-            tc_fence_before();
-            group_sync(0);
-            if (leader) {
-                if (gw) umma_mma_ss(u, at_addr, bt_addr, CP, L::COL_GW1 + k * CP, any_tile);
-                umma_mma<1>(u, bW1T[k], 64, false);
-                umma_commit(u);
-            }
-            umma_wait(u);
-            float de[CP];
-            umma_get_D<CP>(u, de);
-#pragma unroll
-            for (int c = 0; c < C; c += 4)
-                *reinterpret_cast<float4*>(stage + tid * SP + c) = make_float4(de[c], de[c + 1], de[c + 2], de[c + 3]);
-            group_sync(0);
-            if (gplanes) coop_scatter<C, 1>(gplanes, ps, tap_o + k * 512, tap_w + k * 512, pbase, 3 + k, stage, tid);
-            group_sync(0);
+            group_sync(group);
+            coop_scatter_hid(hid, hs, tap_o, tap_w, pbase, k, stage, HS, tg);
+            group_sync(group);
         }
         any_tile = true;
     }
@@ -455,31 +469,94 @@ __global__ void __launch_bounds__(TC_GROUP, 1) k_bwd_tex_tc(const float* __restr
     __syncthreads();
     tc_fence_after();
     if (gw && any_tile) {
-        if (tid < 64) {
+        if (tg < 64) {
             float g[64];
             umma_get_D<64>(u, g, L::COL_GW2);
 #pragma unroll
-            for (int j = 0; j < 64; ++j) if (g[j] != 0.f) atomicAdd(gw + go.g2f + tid * 64 + j, g[j]);
-#pragma unroll 1
-            for (int k = 0; k < 3; ++k) {
-                float g1[CP];
-                umma_get_D<CP>(u, g1, L::COL_GW1 + k * CP);
-#pragma unroll
-                for (int c = 0; c < C; ++c) if (g1[c] != 0.f) atomicAdd(gw + go.g1f + tid * 3 * C + k * C + c, g1[c]);
-            }
+            for (int j = 0; j < 64; ++j) if (g[j] != 0.f) atomicAdd(gw + go.g2f + tg * 64 + j, g[j]);
         }
-        if (tid < 32) {        // warp 0 reads lanes 0..31; rows 0..2 hold dW3
-            float g[64];
-            umma_get_D<64>(u, g, L::COL_GW3);
-            if (tid < 3) {
 #pragma unroll
-                for (int j = 0; j < 64; ++j) if (g[j] != 0.f) atomicAdd(gw + go.g3f + tid * 64 + j, g[j]);
-            }
-        }
+        for (int c = 0; c < 3; ++c) if (dw3[c] != 0.f) atomicAdd(gw + go.g3f + c * 64 + j3, dw3[c]);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc_warp(*tmem_slot, 512);
+    if (warp == 0) tmem_dealloc_warp(*tmem_slot, G * TC_COLS_PER_GROUP);
+}
+
+// ---- dense products with the hidden-gradient planes (once per backward) ----------------------------------------------
+// gplanes[p][3+k][o][c] += Σ_j hid[p][k][o][j] · W1f[j][kC + c]
+template <int C>
+__global__ void __launch_bounds__(256) k_hid_planes(const float* __restrict__ hid, const float* __restrict__ wp, int P, int R,
+                                                   float* __restrict__ gplanes) {
+    TT_SHARED(smem);                          // W1f_k as [64][C]
+    constexpr int U = C / 4;
+    const int k = blockIdx.y;
+    const WOff wo = woff(C);
+    for (int i = threadIdx.x; i < 64 * C; i += 256) { const int j = i / C, c = i % C; smem[i] = __ldg(wp + wo.w1f + j * 3 * C + k * C + c); }
+    __syncthreads();
+    const int64_t RR = (int64_t)R * R, items = (int64_t)P * RR * U;
+    for (int64_t it = (int64_t)blockIdx.x * 256 + threadIdx.x; it < items; it += (int64_t)gridDim.x * 256) {
+        const int64_t cell = it / U; const int ch = (int)(it - cell * U);
+        const int64_t p = cell / RR, o = cell - p * RR;
+        const float* h = hid + ((p * 3 + k) * RR + o) * 64;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+            const float4 hv = ldg4(h + j);
+            any = any || hv.x != 0.f || hv.y != 0.f || hv.z != 0.f || hv.w != 0.f;
+            const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(smem + (j + q) * C + ch * 4);
+                acc.x = fmaf(hh[q], w.x, acc.x); acc.y = fmaf(hh[q], w.y, acc.y);
+                acc.z = fmaf(hh[q], w.z, acc.z); acc.w = fmaf(hh[q], w.w, acc.w);
+            }
+        }
+        if (any) {
+            float4* dst = reinterpret_cast<float4*>(gplanes + ((p * 6 + 3 + k) * RR + o) * C + ch * 4);
+            float4 g = *dst;
+            g.x += acc.x; g.y += acc.y; g.z += acc.z; g.w += acc.w;
+            *dst = g;
+        }
+    }
+}
+// gw.W1f[j][kC + c] += Σ_{p,o} hid[p][k][o][j] · planes[p][3+k][o][c]
+template <int C>
+__global__ void __launch_bounds__(256) k_hid_wgrad(const float* __restrict__ hid, const float* __restrict__ planes, int P,
+                                                  int R, float* __restrict__ gw) {
+    TT_SHARED(smem);
+    constexpr int TX = 64, GS = 65, PS = C + 1, NC = C / 4;
+    float* Gs = smem; float* Ps = smem + TX * GS;
+    const int k = blockIdx.y, j = threadIdx.x & 63, cq = threadIdx.x >> 6;
+    const GOff go = goff(C);
+    const int64_t RR = (int64_t)R * R, spp = (RR + TX - 1) / TX, slabs = (int64_t)P * spp;
+    float acc[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc[i] = 0.f;
+    for (int64_t sl = blockIdx.x; sl < slabs; sl += gridDim.x) {
+        const int64_t p = sl / spp, o0 = (sl - p * spp) * TX;
+        const int nx = (int)(RR - o0 < TX ? RR - o0 : TX);              // texels in this slab
+        const float* h = hid + ((p * 3 + k) * RR + o0) * 64;
+        const float* pl = planes + ((p * 6 + 3 + k) * RR + o0) * C;
+        bool any = false;
+        for (int i = threadIdx.x; i < TX * 64; i += 256) {
+            const float v = i < nx * 64 ? __ldg(h + i) : 0.f;
+            any = any || v != 0.f; Gs[(i >> 6) * GS + (i & 63)] = v;
+        }
+        for (int i = threadIdx.x; i < TX * C; i += 256) Ps[(i / C) * PS + (i % C)] = i < nx * C ? __ldg(pl + i) : 0.f;
+        if (__syncthreads_or(any)) {
+#pragma unroll 4
+            for (int x = 0; x < TX; ++x) {
+                const float g = Gs[x * GS + j];
+#pragma unroll
+                for (int i = 0; i < NC; ++i) acc[i] = fmaf(g, Ps[x * PS + cq + 4 * i], acc[i]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) if (acc[i] != 0.f) atomicAdd(gw + go.g1f + j * 3 * C + k * C + cq + 4 * i, acc[i]);
 }
 
 }  // namespace tt

@@ -179,11 +179,11 @@ def geometry_bwd(planes: Tensor, wpack: Tensor, s: PathScalars, points: Tensor, 
     points = _need(points, "points")
     M = points.shape[1]
     L = _lib()
-    scratch = torch.empty(L.tt_geometry_bwd_scratch_floats(P * M), device=dev, dtype=torch.float32)
+    cfg = _cfg(C_, R, P, 1, s)
+    scratch = torch.empty(L.tt_geometry_bwd_scratch_floats(C.byref(cfg), P * M), device=dev, dtype=torch.float32)
     gplanes = torch.zeros_like(planes) if need_planes else None
     gw = torch.zeros(L.tt_wgrad_floats(C_), device=dev, dtype=torch.float32) if need_w else None
     gs = [None if g is None else _need(g, "grad") for g in (g_sdf, g_features, g_normal, g_sdf_grad)]
-    cfg = _cfg(C_, R, P, 1, s)
     with torch.cuda.device(dev):
         _cabi.check(L, L.tt_geometry_bwd(_ptr(planes), _ptr(wpack), C.byref(cfg), _ptr(points), M,
                                          *[_ptr(g) for g in gs], _ptr(scratch), _ptr(gplanes), _ptr(gw),
@@ -263,12 +263,12 @@ def render_bwd(planes, wpack, s: PathScalars, rays_o, rays_d, rays_per_cache, t_
     n = o.shape[0]
     t0, t1, stride, S = _intervals(t_starts, t_ends)
     L = _lib()
-    scratch = torch.empty(L.tt_render_bwd_scratch_floats(n, S), device=dev, dtype=torch.float32)
+    cfg = _cfg(C_, R, P, rays_per_cache, s)
+    scratch = torch.empty(L.tt_render_bwd_scratch_floats(C.byref(cfg), n, S), device=dev, dtype=torch.float32)
     gplanes = torch.zeros_like(planes) if need_planes else None
     gw = torch.zeros(L.tt_wgrad_floats(C_), device=dev, dtype=torch.float32) if need_w else None
     gis = torch.zeros(1, device=dev, dtype=torch.float32) if need_inv_std else None
     opt = [None if g is None else _need(g, "grad") for g in (g_sdf, g_sdf_grad, g_normal, g_features, g_weights)]
-    cfg = _cfg(C_, R, P, rays_per_cache, s)
     with torch.cuda.device(dev):
         _cabi.check(L, L.tt_render_bwd(_ptr(planes), _ptr(wpack), C.byref(cfg), _ptr(o), _ptr(d), n, _ptr(t0),
                                        _ptr(t1), stride, S, _ptr(saved["acc"]), _ptr(saved["sdf"]),
