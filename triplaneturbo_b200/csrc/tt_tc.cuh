@@ -362,39 +362,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
                     *reinterpret_cast<float4*>(stage + tg * SP + c) = make_float4(de[c], de[c + 1], de[c + 2], de[c + 3]);
             }
             group_sync(group);
-            {   // cooperative pass: d(de · f_k)/d(ix,iy) per plane.  SEG lanes share one point (one 16-byte channel
-                // chunk each); the partial dot products are reduced with shuffles inside the segment.
-                constexpr int U = C / 4, SEG = U > 8 ? 16 : 8, PW = 32 / SEG;
-                const int lane = tid & 31, seg = lane / SEG, ch = lane % SEG;
+            {   // cooperative pass: d(de · f_k)/d(ix,iy) per plane.  4 lanes share one point: lane sl takes the 16-byte
+                // channel chunks sl, sl+4, ... of every tap and accumulates its partial dot products before the
+                // two-step shuffle reduction over the 4 lanes (8 points per warp iteration).
+                constexpr int U = C / 4, STEPS = (U + 3) / 4;
+                const int lane = tid & 31, seg = lane >> 2, sl = lane & 3;
                 const int wpt0 = (tg >> 5) * 32;
 #pragma unroll 1
-                for (int r = 0; r < 32 / PW; ++r) {
-                    const int pt = wpt0 + r * PW + seg;
-                    float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (ch < U) {
-                        const float4 dv = *reinterpret_cast<const float4*>(stage + pt * SP + ch * 4);
-                        const float* base = planes + (size_t)pbase[pt] * 6 * ps + ch * 4;
-                        float A[12];
-                        float4 q[12];
+                for (int r = 0; r < 4; ++r) {
+                    const int pt = wpt0 + r * 8 + seg;
+                    int o[12];
 #pragma unroll
-                        for (int t = 0; t < 12; ++t) q[t] = ldg4(base + (size_t)(t >> 2) * ps + (size_t)tap_o[pt * 12 + t] * C);
+                    for (int t = 0; t < 12; t += 4) {
+                        const int4 o4 = *reinterpret_cast<const int4*>(tap_o + pt * 12 + t);
+                        o[t] = o4.x; o[t + 1] = o4.y; o[t + 2] = o4.z; o[t + 3] = o4.w;
+                    }
+                    const float* pbp = planes + (size_t)pbase[pt] * 6 * ps;
+                    float A[12];
 #pragma unroll
-                        for (int t = 0; t < 12; ++t)
-                            A[t] = (dv.x * q[t].x + dv.y * q[t].y + dv.z * q[t].z + dv.w * q[t].w) * tap_v[pt * 12 + t];
+                    for (int t = 0; t < 12; ++t) A[t] = 0.f;
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            const float wx0 = tap_f[pt * 12 + k * 4], wx1 = tap_f[pt * 12 + k * 4 + 1];
-                            const float wy0 = tap_f[pt * 12 + k * 4 + 2], wy1 = tap_f[pt * 12 + k * 4 + 3];
-                            part[k * 2] = (A[k * 4 + 1] - A[k * 4]) * wy0 + (A[k * 4 + 3] - A[k * 4 + 2]) * wy1;
-                            part[k * 2 + 1] = (A[k * 4 + 2] - A[k * 4]) * wx0 + (A[k * 4 + 3] - A[k * 4 + 1]) * wx1;
+                    for (int st = 0; st < STEPS; ++st) {
+                        const int ch = sl + 4 * st;
+                        if (ch < U) {
+                            const float4 dv = *reinterpret_cast<const float4*>(stage + pt * SP + ch * 4);
+                            const float* base = pbp + ch * 4;
+                            float4 q[12];
+#pragma unroll
+                            for (int t = 0; t < 12; ++t) q[t] = ldg4(base + (size_t)(t >> 2) * ps + (size_t)o[t] * C);
+#pragma unroll
+                            for (int t = 0; t < 12; ++t)
+                                A[t] = fmaf(dv.x, q[t].x, fmaf(dv.y, q[t].y, fmaf(dv.z, q[t].z, fmaf(dv.w, q[t].w, A[t]))));
                         }
+                    }
+                    float part[6];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float4 tv = *reinterpret_cast<const float4*>(tap_v + pt * 12 + k * 4);
+                        const float4 tf = *reinterpret_cast<const float4*>(tap_f + pt * 12 + k * 4);     // wx0 wx1 wy0 wy1
+                        const float a0 = A[k * 4] * tv.x, a1 = A[k * 4 + 1] * tv.y, a2 = A[k * 4 + 2] * tv.z, a3 = A[k * 4 + 3] * tv.w;
+                        part[k * 2] = (a1 - a0) * tf.z + (a3 - a2) * tf.w;
+                        part[k * 2 + 1] = (a2 - a0) * tf.x + (a3 - a1) * tf.y;
                     }
 #pragma unroll
                     for (int qd = 0; qd < 6; ++qd) {
                         float v = part[qd];
-#pragma unroll
-                        for (int off = SEG / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                        if (ch == 0) nacc[pt * 6 + qd] = v;
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        if (sl == 0) nacc[pt * 6 + qd] = v;
                     }
                 }
             }

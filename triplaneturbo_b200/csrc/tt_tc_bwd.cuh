@@ -26,14 +26,15 @@ __device__ __forceinline__ void coop_scatter(float* __restrict__ gplanes, size_t
         const float4 v = *reinterpret_cast<const float4*>(stage + pt * SP + ch * 4);
         float* base = gplanes + (size_t)pbase[pt] * 6 * ps + (size_t)plane0 * ps + ch * 4;
 #pragma unroll
-        for (int k = 0; k < NPL; ++k)
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int o = tap_o[pt * NT + k * 4 + t];
-                const float ww = tap_w[pt * NT + k * 4 + t];
-                if (ww != 0.f)
-                    red_add4(base + k * ps + (size_t)o * C, make_float4(v.x * ww, v.y * ww, v.z * ww, v.w * ww));
-            }
+        for (int k = 0; k < NPL; ++k) {
+            const int4 o4 = *reinterpret_cast<const int4*>(tap_o + pt * NT + k * 4);
+            const float4 w4 = *reinterpret_cast<const float4*>(tap_w + pt * NT + k * 4);
+            float* pb = base + k * ps;
+            if (w4.x != 0.f) red_add4(pb + (size_t)o4.x * C, make_float4(v.x * w4.x, v.y * w4.x, v.z * w4.x, v.w * w4.x));
+            if (w4.y != 0.f) red_add4(pb + (size_t)o4.y * C, make_float4(v.x * w4.y, v.y * w4.y, v.z * w4.y, v.w * w4.y));
+            if (w4.z != 0.f) red_add4(pb + (size_t)o4.z * C, make_float4(v.x * w4.z, v.y * w4.z, v.z * w4.z, v.w * w4.z));
+            if (w4.w != 0.f) red_add4(pb + (size_t)o4.w * C, make_float4(v.x * w4.w, v.y * w4.w, v.z * w4.w, v.w * w4.w));
+        }
     }
 }
 

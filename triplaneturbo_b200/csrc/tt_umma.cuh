@@ -33,7 +33,8 @@ __device__ __forceinline__ int btile_off(int n, int k, int K) {     // float off
     return ((n & 7) * 16 + (n >> 3) * ((K >> 2) * 128) + (k >> 2) * 128 + (k & 3) * 4) >> 2;
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-// round-to-nearest tf32 (single-pass operands: gradients), ties away from zero
+// round-to-nearest tf32 (single-pass operands: gradients), ties away from zero.  (Two full-rate integer ops;
+// cvt.rna.tf32.f32 is one instruction but runs on the conversion pipe: measured 5 % slower in k_bwd_geo_tc.)
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 // Operand tiles of the weight-gradient contractions (K = the tile's 128 points): element (row r, point p) of an
