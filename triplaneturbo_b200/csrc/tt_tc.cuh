@@ -86,26 +86,11 @@ __device__ __forceinline__ bool point_empty(const float (&x)[3], float radius, i
     }
     return true;
 }
-// append `id` to a list from every lane with `take` set (all 32 lanes of the warp must call this)
-__device__ __forceinline__ void warp_append(bool take, int id, int* list, int* count) {
-#ifndef TT_EMUL
-    const unsigned m = __ballot_sync(0xffffffffu, take);
-    if (m) {
-        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (take) list[base + __popc(m & ((1u << lane) - 1u))] = id;
-    }
-#else
-    if (take) list[atomicAdd(count, 1)] = id;
-#endif
-}
-
 // Ordered block-level reservation in a list: every thread of the block asks for n slots; slices are handed out in
 // thread order inside ONE contiguous range per block (a single atomicAdd), so that the list keeps the sample order
-// of the block (ray-major).  A warp-aggregated append (above) interleaves 32-entry chunks of every resident warp of
-// the GPU, which scatters a 128-point tile over several views and defeats L1/L2.  All threads must call.
+// of the block (ray-major).  (A warp-aggregated append interleaves 32-entry chunks of every resident warp of the GPU,
+// which scatters a 128-point tile over several views: measured 123 GB of DRAM reads per backward launch.)  All threads
+// must call.
 template <int NTHREADS>
 __device__ __forceinline__ int block_reserve(int n, int* counter) {
     __shared__ int s_cnt[NTHREADS / 32 + 1];

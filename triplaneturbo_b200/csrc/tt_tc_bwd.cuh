@@ -38,12 +38,61 @@ __device__ __forceinline__ void coop_scatter(float* __restrict__ gplanes, size_t
     }
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#ifndef TT_EMUL
+// Run-length merged scatter.  The points of a tile are consecutive samples of a ray (ray-major lists); inside the band
+// the importance sampler concentrates on, ten or more consecutive samples fall into the same texel cell, so their
+// contributions to a texel are summed in registers and leave the SM as ONE vector reduction.  Thread (ch, r) owns the
+// 16-byte channel chunk ch of every texel and walks the r-th contiguous range of the tile's points with one pending
+// (texel, float4) per tap slot; a pending entry is flushed when the slot moves to another texel.  The reductions of the
+// CH lanes of a range stay one contiguous run of a texel.
+//   dst + prompt * prompt_stride + k * plane_stride + texel * texel_stride + ch * 4   (floats)
+template <int CH, int NPL>
+__device__ __forceinline__ void coop_scatter_rl(float* __restrict__ dst, size_t prompt_stride, size_t plane_stride,
+                                                int texel_stride, const int* tap_o, const float* tap_w,
+                                                const uint32_t* pbase, const float* stage, int stage_stride, int tg) {
+    constexpr int NR = TC_GROUP / CH, RL = (TC_GROUP + NR - 1) / NR, NT = 4 * NPL;
+    const int ch = tg % CH, r = tg / CH;
+    if (r >= NR) return;
+    int cur[NT];
+    float4 acc[NT];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-#endif
-    return v;
+    for (int s = 0; s < NT; ++s) { cur[s] = -1; acc[s] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    const int p0 = r * RL, p1 = p0 + RL < TC_GROUP ? p0 + RL : TC_GROUP;
+    uint32_t pb_cur = p0 < TC_GROUP ? pbase[p0] : 0u;
+    float* base = dst + (size_t)pb_cur * prompt_stride + ch * 4;
+#pragma unroll 1
+    for (int p = p0; p < p1; ++p) {
+        const uint32_t pb = pbase[p];
+        if (pb != pb_cur) {                      // the tile crosses into another prompt's planes (rare): flush everything
+#pragma unroll
+            for (int s = 0; s < NT; ++s) {
+                if (cur[s] >= 0) red_add4(base + (size_t)(s >> 2) * plane_stride + (size_t)cur[s] * texel_stride, acc[s]);
+                cur[s] = -1;
+            }
+            pb_cur = pb; base = dst + (size_t)pb_cur * prompt_stride + ch * 4;
+        }
+        const float4 v = *reinterpret_cast<const float4*>(stage + p * stage_stride + ch * 4);
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int4 o4 = *reinterpret_cast<const int4*>(tap_o + p * NT + k * 4);
+            const float4 w4 = *reinterpret_cast<const float4*>(tap_w + p * NT + k * 4);
+            const int oo[4] = {o4.x, o4.y, o4.z, o4.w};
+            const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int s = k * 4 + t;
+                const bool val = ww[t] != 0.f, same = val && oo[t] == cur[s];
+                if (val && !same && cur[s] >= 0) red_add4(base + (size_t)k * plane_stride + (size_t)cur[s] * texel_stride, acc[s]);
+                if (val) {
+                    const float4 a = same ? acc[s] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc[s] = make_float4(fmaf(v.x, ww[t], a.x), fmaf(v.y, ww[t], a.y), fmaf(v.z, ww[t], a.z), fmaf(v.w, ww[t], a.w));
+                    cur[s] = oo[t];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NT; ++s)
+        if (cur[s] >= 0) red_add4(base + (size_t)(s >> 2) * plane_stride + (size_t)cur[s] * texel_stride, acc[s]);
 }
 
 // ================================================================================================ SDF branch
@@ -174,7 +223,9 @@ k_bwd_geo_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
                 *reinterpret_cast<float4*>(stage + tg * SP + c) = make_float4(de[c], de[c + 1], de[c + 2], de[c + 3]);
         }
         group_sync(group);
-        if (gplanes) coop_scatter<C, 3>(gplanes, ps, tap_o, tap_om, pbase, 0, stage, tg);     // d L / d texel = de · ω
+        // d L / d texel = de · ω  (plain scatter: with 12 tap slots the run-length merged variant measured 4 % slower on
+        // the synthetic benchmark planes, whose noisy SDF spreads the fine samples; it wins for the 64-wide colour scatter)
+        if (gplanes) coop_scatter<C, 3>(gplanes, ps, tap_o, tap_om, pbase, 0, stage, tg);
         group_sync(group);
         coop_gather<C, 3>(planes, ps, tap_o, tap_om, pbase, 0, stage, tg);                    // ẽ = Σ ω · texel
         group_sync(group);
@@ -269,24 +320,6 @@ struct BwdTexSmem {
     static constexpr uint32_t COL_GW2 = 64;
     static_assert(128 * (C + 4) <= wg_tile_floats(64) && 128 * HS <= wg_tile_floats(64), "stage must fit in the B tile");
 };
-
-// scatter the staged 64-wide rows into the hidden-gradient planes hid[P][3][R*R][64]
-__device__ __forceinline__ void coop_scatter_hid(float* __restrict__ hid, size_t hs, const int* tap_o, const float* tap_w,
-                                                 const uint32_t* pbase, int k, const float* stage, int stride, int tg) {
-#pragma unroll 1
-    for (int j = 0; j < 16; ++j) {
-        const int item = tg + TC_GROUP * j;
-        const int pt = item >> 4, ch = item & 15;
-        const float4 v = *reinterpret_cast<const float4*>(stage + pt * stride + ch * 4);
-        float* base = hid + ((size_t)pbase[pt] * 3 + k) * hs + ch * 4;
-        const int4 o4 = *reinterpret_cast<const int4*>(tap_o + pt * 4);
-        const float4 w4 = *reinterpret_cast<const float4*>(tap_w + pt * 4);
-        if (w4.x != 0.f) red_add4(base + (size_t)o4.x * 64, make_float4(v.x * w4.x, v.y * w4.x, v.z * w4.x, v.w * w4.x));
-        if (w4.y != 0.f) red_add4(base + (size_t)o4.y * 64, make_float4(v.x * w4.y, v.y * w4.y, v.z * w4.y, v.w * w4.y));
-        if (w4.z != 0.f) red_add4(base + (size_t)o4.z * 64, make_float4(v.x * w4.z, v.y * w4.z, v.z * w4.z, v.w * w4.z));
-        if (w4.w != 0.f) red_add4(base + (size_t)o4.w * 64, make_float4(v.x * w4.w, v.y * w4.w, v.z * w4.w, v.w * w4.w));
-    }
-}
 
 template <int C>
 __global__ void __launch_bounds__(BwdTexSmem<C>::G * TC_GROUP, 1)
@@ -461,7 +494,7 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
                 *reinterpret_cast<float4*>(tap_w + tg * 4) = w4;
             }
             group_sync(group);
-            coop_scatter_hid(hid, hs, tap_o, tap_w, pbase, k, stage, HS, tg);
+            coop_scatter_rl<16, 1>(hid + (size_t)k * hs, 3 * hs, 0, 64, tap_o, tap_w, pbase, stage, HS, tg);
             group_sync(group);
         }
         any_tile = true;
