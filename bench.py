@@ -299,7 +299,12 @@ def main():
                 "algorithmic_flops_per_launch": dom_flops,
                 "step_tflops": fl["step_survey"] * n_rays * args.steps / (ms_total * 1e-3) / 1e12,
                 "hbm_compulsory_gbs": (planes_bytes * 2 + n_rays * 80) * args.steps / (ms_total * 1e-3) / 1e9,
-                "kernels_ms": {k: round(v, 4) for k, v in kern_ms.items()}}
+                # measured DRAM bytes of the dominant kernel / its live duration vs the measured HBM peak: the path is
+                # not HBM-bound (it is bound by the L1/L2 gather and reduction path)
+                "hbm_gbs_achieved": (traffic / (kern_ms[dom] * 1e-3) / 1e9) if traffic else None,
+                "hbm_peak_gbs": peaks.get("hbm_gbs"),
+                "kernels_ms": {k: round(v, 4) for k, v in kern_ms.items()},
+                "kernels_ms_per_step": {k: round(v / args.steps, 4) for k, v in kern_tot.items()}}
 
     cpu = None
     if not args.no_cpu_baseline and not args.profile:
