@@ -763,21 +763,25 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
     if (!aligned16(planes) || !aligned16(wpack)) return fail(TT_E_ALIGN, "planes/wpack must be 16-byte aligned%s", "");
     const int64_t N = (int64_t)cfg->P * M;
     if (N == 0) return TT_OK;
-    if (g_impl == 1 && !deformation && N < 2147483647LL) {
+    if (g_impl == 1 && !(deformation && (normal || sdf_grad)) && N < 2147483647LL) {
         bool done = false;
         TT_DISPATCH_C(cfg->C, {
             const size_t smg_n = (size_t)GeoSmem<kC, true>::TOTAL * 4, smg = (size_t)GeoSmem<kC, false>::TOTAL * 4;
+            const size_t smg_d = (size_t)GeoSmem<kC, false, true>::TOTAL * 4;
             const size_t smt = (size_t)TexSmem<kC>::TOTAL * 4;
             const bool want_n = normal || sdf_grad;
-            if ((want_n ? smg_n : smg) <= kMaxSmem && smt <= kMaxSmem) {
+            if ((deformation ? smg_d : want_n ? smg_n : smg) <= kMaxSmem && smt <= kMaxSmem) {
                 TcSrc src{}; src.mode = points ? 0 : 3; src.points = points; src.M = M; src.grid_res = grid_res;
-                if (sdf || sdf_orig || want_n) {
-                    if (want_n) {
+                if (sdf || sdf_orig || want_n || deformation) {
+                    if (deformation) {      // field query of the mesh paths: SDF + deformation decoders on one gather
+                        if (int e = set_smem(k_geo_tc<kC, false, true>, smg_d)) return e;
+                        TT_LAUNCH((k_geo_tc<kC, false, true>), tc_grid(N), TC_THREADS, smg_d, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr, deformation);
+                    } else if (want_n) {
                         if (int e = set_smem(k_geo_tc<kC, true>, smg_n)) return e;
-                        TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg_n, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr);
+                        TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg_n, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr, (float*)nullptr);
                     } else {
                         if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
-                        TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr);
+                        TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr, (float*)nullptr);
                     }
                     if (int e = check_launch("k_geo_tc")) return e;
                 }
@@ -834,7 +838,7 @@ int tt_importance_sample(const float* planes, const float* wpack, const tt_confi
                 if (int e = check_launch("k_classify")) return e;
                 src.index = list; src.count = lcount;
                 if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
-                TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, (float*)nullptr, (float*)nullptr, (float*)nullptr, (uint64_t*)nullptr);
+                TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, (float*)nullptr, (float*)nullptr, (float*)nullptr, (uint64_t*)nullptr, (float*)nullptr);
                 if (int e = check_launch("k_geo_tc")) return e;
                 TT_LAUNCH(k_sampler_post, (unsigned)blocks, TPB, 0, (cudaStream_t)stream, *cfg, n_rays, n_imp, n_fine, (const float*)sdf, jitter0, jitter1, cdf, t_vals);
                 if (int e = check_launch("k_sampler_post")) return e;
@@ -897,7 +901,7 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
                 if (int e = check_launch("k_classify")) return e;
                 src.index = live; src.count = count + 1;
                 if (int e = set_smem(k_geo_tc<kC, true>, smg)) return e;
-                TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, src, N, p_sdf, sdf_orig, p_grad, (float*)nullptr, masks);
+                TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, src, N, p_sdf, sdf_orig, p_grad, (float*)nullptr, masks, (float*)nullptr);
                 if (int e = check_launch("k_geo_tc")) return e;
                 src.index = nullptr; src.count = nullptr;
                 TT_LAUNCH(k_weights, (unsigned)((n_rays + RAY_WARPS - 1) / RAY_WARPS), RAY_WARPS * 32, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, acc, weights, p_trans, normal,
@@ -1069,7 +1073,7 @@ int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cf
                 TcSrc ts{}; ts.mode = 0; ts.points = points; ts.M = M;
                 if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
                 TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, ts, N, (float*)nullptr, (float*)nullptr,
-                          (float*)nullptr, (float*)nullptr, masks);
+                          (float*)nullptr, (float*)nullptr, masks, (float*)nullptr);
                 if (int e = check_launch("k_geo_tc")) return e;
                 if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
                 TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, ts, N, (float*)nullptr, masks);

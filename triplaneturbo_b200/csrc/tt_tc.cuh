@@ -205,14 +205,17 @@ __device__ __forceinline__ void coop_gather(const float* __restrict__ planes, si
 __device__ __forceinline__ int tap_off(int o) { return o < 0 ? 0 : o; }
 
 // shared-memory plan of k_geo_tc (float offsets)
-template <int C, bool NORMAL>
+template <int C, bool NORMAL, bool DEFORM = false>
 struct GeoSmem {
     static constexpr int CP = (C + 15) / 16 * 16;
     static constexpr int W1H = 0, W1L = W1H + 64 * C, W2H = W1L + 64 * C, W2L = W2H + 4096;
     static constexpr int W2TH = W2L + 4096, W2TL = W2TH + (NORMAL ? 4096 : 0);
     static constexpr int W1TH = W2TL + (NORMAL ? 4096 : 0), W1TL = W1TH + (NORMAL ? CP * 64 : 0);
     static constexpr int W3 = W1TL + (NORMAL ? CP * 64 : 0);
-    static constexpr int GROUP0 = W3 + 64;
+    // deformation MLP (same encoding, second decoder): W1d, W2d hi/lo tiles and the [3][64] head
+    static constexpr int D1H = W3 + 64, D1L = D1H + (DEFORM ? 64 * C : 0), D2H = D1L + (DEFORM ? 64 * C : 0);
+    static constexpr int D2L = D2H + (DEFORM ? 4096 : 0), D3 = D2L + (DEFORM ? 4096 : 0);
+    static constexpr int GROUP0 = D3 + (DEFORM ? 192 : 0);
     // per group
     static constexpr int TAP_O = 0, TAP_W = TAP_O + 128 * 12, TAP_F = TAP_W + 128 * 12;      // ints, floats, factors
     static constexpr int TAP_V = TAP_F + (NORMAL ? 128 * 12 : 0);                              // validity (1 / 0)
@@ -223,13 +226,13 @@ struct GeoSmem {
     static constexpr int TOTAL = GROUP0 + TC_GROUPS * GROUP_FLOATS + 16;     // + mbarriers, tmem slot
 };
 
-template <int C, bool NORMAL>
+template <int C, bool NORMAL, bool DEFORM = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restrict__ planes, const float* __restrict__ wp,
                                                          tt_config cfg, TcSrc src, int64_t N, float* sdf_o,
                                                          float* sdf_orig_o, float* grad_o, float* normal_o,
-                                                         uint64_t* masks_o) {
+                                                         uint64_t* masks_o, float* deform_o = nullptr) {
     TT_SHARED(smem);
-    using L = GeoSmem<C, NORMAL>;
+    using L = GeoSmem<C, NORMAL, DEFORM>;
     constexpr int CP = L::CP, SP = C + 4;
     const int tid = threadIdx.x, group = tid / TC_GROUP, tg = tid % TC_GROUP, warp = tid >> 5;
     const WOff wo = woff(C);
@@ -241,6 +244,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
         btile_fill(smem + L::W1TH, smem + L::W1TL, CP, 64, [&](int n, int k) { return n < C ? __ldg(wp + wo.w1s + k * C + n) : 0.f; }, tid, TC_THREADS);
     }
     if (tid < 64) smem[L::W3 + tid] = __ldg(wp + wo.w3s + tid);
+    if (DEFORM) {
+        btile_fill(smem + L::D1H, smem + L::D1L, 64, C, [&](int n, int k) { return __ldg(wp + wo.w1d + n * C + k); }, tid, TC_THREADS);
+        btile_fill(smem + L::D2H, smem + L::D2L, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2d + n * 64 + k); }, tid, TC_THREADS);
+        if (tid < 192) smem[L::D3 + tid] = __ldg(wp + wo.w3d + tid);
+    }
     uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::GROUP0 + TC_GROUPS * L::GROUP_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + TC_GROUPS);
     if (tid == 0) for (int g = 0; g < TC_GROUPS; ++g) mbar_init(mbars + g);
@@ -254,6 +262,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
     u.lane_base = (uint32_t)((warp & 3) * 32) << 16;
     u.mbar = smem_u32(mbars + group); u.phase = 0; u.group = group;
     const bool leader = tg == 0;
+    const BTile bD1 = btile_make(smem + L::D1H, smem + L::D1L, 64, C);
+    const BTile bD2 = btile_make(smem + L::D2H, smem + L::D2L, 64, 64);
     const BTile bW1 = btile_make(smem + L::W1H, smem + L::W1L, 64, C);
     const BTile bW2 = btile_make(smem + L::W2H, smem + L::W2L, 64, 64);
     const BTile bW2T = btile_make(smem + L::W2TH, smem + L::W2TL, 64, 64);
@@ -331,6 +341,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
             if (sdf_orig_o) sdf_orig_o[id] = s;
             if (sdf_o) sdf_o[id] = s + (nrm - cfg.sdf_bias_radius);
             if (masks_o) { masks_o[id * 4 + 2] = m1; masks_o[id * 4 + 3] = m2; }     // ReLU masks for the backward
+        }
+        if (DEFORM) {     // deformation decoder on the same encoding (still in the stage): 32->64->64->3, 3xTF32
+            const float* w3d = smem + L::D3;
+            {
+                float e[C];
+#pragma unroll
+                for (int c = 0; c < C; c += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(stage + tg * SP + c);
+                    e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
+                }
+                umma_layer<C, 64, 3>(u, leader, e, bD1, d);
+            }
+            {
+                float h[64];
+#pragma unroll
+                for (int j = 0; j < 64; ++j) h[j] = fmaxf(d[j], 0.f);
+                umma_layer<64, 64, 3>(u, leader, h, bD2, d);
+            }
+            float df[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const float h = fmaxf(d[j], 0.f);
+                df[0] = fmaf(h, w3d[j], df[0]); df[1] = fmaf(h, w3d[64 + j], df[1]); df[2] = fmaf(h, w3d[128 + j], df[2]);
+            }
+            if (valid && deform_o) { deform_o[id * 3] = df[0]; deform_o[id * 3 + 1] = df[1]; deform_o[id * 3 + 2] = df[2]; }
         }
         if (NORMAL) {
             {   // unit-seed adjoint: a2 = m2 ⊙ w3 ; a1 = m1 ⊙ (W2ᵀ a2) ; de = W1ᵀ a1
