@@ -160,6 +160,12 @@ def main():
         return reference_arm(args, wl, rank)
     args.warmup = 1 if args.profile else max(args.warmup, 3)
 
+    # Libraries (NCCL prints its version banner) may write to fd 1: keep stdout for the ONE JSON line by pointing fd 1
+    # at stderr until the result is printed.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -314,6 +320,8 @@ def main():
                "sample": f"2 steps of 1 prompt x 1 view x {hw}x{hw} rays at {args.workload} plane/sample sizes "
                          f"(oracle/, torch CPU, {os.cpu_count()} threads)"}
 
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -324,6 +332,8 @@ def main():
         "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}))
+    sys.stdout.flush()
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
