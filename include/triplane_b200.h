@@ -137,6 +137,28 @@ int tt_importance_sample(const float* planes, const float* wpack, const tt_confi
                          int n_imp, int n_fine, const float* jitter0, const float* jitter1,
                          float* scratch, float* t_vals, void* stream);
 
+/* ---- stand-alone plane sampler ------------------------------------------------------------
+ * Replaces, as an operator of its own: grid_sample / sample_from_planes
+ * (custom/triplaneturbo/models/geometry/utils.py:21-24,127-145), the custom autograd pair
+ * _GridSample2dForward / _GridSample2dBackward (extern/grid_sample_gradfix/cuda_gridsample.py:22-79) and the
+ * second-derivative kernel grid_sampler_2d_grad2_kernel (extern/grid_sample_gradfix/gridsample_cuda.cu:27-210);
+ * bilinear, zeros padding, align_corners = False.
+ * planes [N*K][H][W][C] channel-last (tt_to_channel_last converts [B][C][HW] NCHW data; 1 <= K <= 4, C % 4 == 0),
+ * grid [N*K][M][2] normalised (x -> W, y -> H), out [N][M][OS]: the K planes are summed (concat = 0, OS = C,
+ * interpolate_feat "v1") or concatenated (concat = 1, OS = K*C, "v2").
+ * bwd: g_planes (same layout as planes) is ACCUMULATED into, g_grid [N*K][M][2] is written; both nullable.
+ * bwdbwd(gg_planes, gg_grid = gradients arriving at bwd's two outputs, nullable) -> gg_out [N][M][OS] (written),
+ * g_planes (accumulated), g_grid (written); all nullable. */
+int tt_to_channel_last(const float* src, int64_t B, int C, int64_t HW, float* dst, void* stream);
+int tt_from_channel_last(const float* src, int64_t B, int C, int64_t HW, float* dst, void* stream);
+int tt_sample_planes_fwd(const float* planes, int N, int K, int C, int H, int W, const float* grid, int64_t M,
+                         int concat, float* out, void* stream);
+int tt_sample_planes_bwd(const float* planes, int N, int K, int C, int H, int W, const float* grid, int64_t M,
+                         int concat, const float* g_out, float* g_planes, float* g_grid, void* stream);
+int tt_sample_planes_bwdbwd(const float* planes, int N, int K, int C, int H, int W, const float* grid, int64_t M,
+                            int concat, const float* g_out, const float* gg_planes, const float* gg_grid,
+                            float* gg_out, float* g_planes, float* g_grid, void* stream);
+
 /* ---- fused march + decoder MLPs + NeuS alpha + compositing -------------------------------
  * Replaces: GenerativeSpaceSDFVolumeRenderer._forward from sample positions to the per-ray
  * accumulators (…sdf_volume_renderer.py:317-431,466-472), i.e. geometry.forward with analytic

@@ -161,3 +161,45 @@ class Emul:
                                      *[ptr(x) for x in opt], rgb_scale, ptr(scratch),
                                      ptr(gplanes), ptr(gw), ptr(gis), None), "render_bwd")
         return gplanes, self.split_wgrad(gw, cfg.C), float(gis[0])
+
+    # ---- stand-alone plane sampler (tt_sampler.cuh) ------------------------------------------------------------
+    def to_channel_last(self, x):
+        x = f32(x); B, C_, HW = x.shape
+        y = aligned_zeros((B, HW, C_))
+        self.ok(self.L.tt_to_channel_last(ptr(x), B, C_, HW, ptr(y), None), "to_channel_last")
+        return y
+
+    def from_channel_last(self, y):
+        y = f32(y); B, HW, C_ = y.shape
+        x = aligned_zeros((B, C_, HW))
+        self.ok(self.L.tt_from_channel_last(ptr(y), B, C_, HW, ptr(x), None), "from_channel_last")
+        return x
+
+    @staticmethod
+    def _al(a):
+        out = aligned_zeros(np.shape(a)); out[...] = a
+        return out
+
+    def sample_fwd(self, planes, grid, K, concat):
+        planes, grid = self._al(planes), f32(grid)
+        NK, H, W, C_ = planes.shape; N, M = NK // K, grid.shape[1]
+        out = aligned_zeros((N, M, K * C_ if concat else C_))
+        self.ok(self.L.tt_sample_planes_fwd(ptr(planes), N, K, C_, H, W, ptr(grid), M, int(concat), ptr(out), None), "sample_fwd")
+        return out
+
+    def sample_bwd(self, planes, grid, K, concat, g_out):
+        planes, grid, g_out = self._al(planes), f32(grid), self._al(g_out)
+        NK, H, W, C_ = planes.shape; N, M = NK // K, grid.shape[1]
+        gp, gg = aligned_zeros(planes.shape), np.zeros_like(grid)
+        self.ok(self.L.tt_sample_planes_bwd(ptr(planes), N, K, C_, H, W, ptr(grid), M, int(concat), ptr(g_out), ptr(gp), ptr(gg), None), "sample_bwd")
+        return gp, gg
+
+    def sample_bwdbwd(self, planes, grid, K, concat, g_out, gg_planes, gg_grid):
+        planes, grid, g_out = self._al(planes), f32(grid), self._al(g_out)
+        ggp = None if gg_planes is None else self._al(gg_planes)
+        ggg = None if gg_grid is None else f32(gg_grid)
+        NK, H, W, C_ = planes.shape; N, M = NK // K, grid.shape[1]
+        ggo, gp, gg = aligned_zeros(g_out.shape), aligned_zeros(planes.shape), np.zeros_like(grid)
+        self.ok(self.L.tt_sample_planes_bwdbwd(ptr(planes), N, K, C_, H, W, ptr(grid), M, int(concat), ptr(g_out), ptr(ggp), ptr(ggg),
+                                               ptr(ggo), ptr(gp), ptr(gg), None), "sample_bwdbwd")
+        return ggo, gp, gg

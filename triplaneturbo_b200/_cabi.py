@@ -51,6 +51,11 @@ SIGNATURES = {
     "tt_render_bwd_scratch_floats": (C.c_size_t, [_cfgp, i64, C.c_int]),
     "tt_render_bwd": (C.c_int, [fp, fp, _cfgp, fp, fp, i64, fp, fp, i64, C.c_int] + [fp] * 6 + [fp] * 6 +
                       [C.c_float, fp, fp, fp, fp, fp]),
+    "tt_to_channel_last": (C.c_int, [fp, i64, C.c_int, i64, fp, fp]),
+    "tt_from_channel_last": (C.c_int, [fp, i64, C.c_int, i64, fp, fp]),
+    "tt_sample_planes_fwd": (C.c_int, [fp] + [C.c_int] * 5 + [fp, i64, C.c_int, fp, fp]),
+    "tt_sample_planes_bwd": (C.c_int, [fp] + [C.c_int] * 5 + [fp, i64, C.c_int, fp, fp, fp, fp]),
+    "tt_sample_planes_bwdbwd": (C.c_int, [fp] + [C.c_int] * 5 + [fp, i64, C.c_int] + [fp] * 7),
     "tt_composite_fwd": (C.c_int, [fp, fp, i64, C.c_int, C.c_int, fp, fp, fp, fp]),
     "tt_composite_bwd": (C.c_int, [fp, fp, fp, fp, fp, i64, C.c_int, C.c_int, fp, fp, fp]),
 }

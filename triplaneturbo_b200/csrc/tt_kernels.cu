@@ -4,6 +4,7 @@
 #include "tt_tc.cuh"
 #include "tt_tc_bwd.cuh"
 #include "tt_rays.cuh"
+#include "tt_sampler.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -1102,6 +1103,75 @@ int tt_composite_bwd(const float* alphas, const float* values, const float* tran
     TT_LAUNCH(k_composite_bwd, (unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream, alphas, values, trans, g_out, g_weights,
         n_rays, S, D, g_alphas, g_values);
     return check_launch("tt_composite_bwd");
+}
+
+// ---- stand-alone plane sampler (tt_sampler.cuh) -----------------------------------------------------------------------
+static int sample_args(const char* who, const float* planes, int N, int K, int C, int H, int W, const float* grid, int64_t M,
+                       int concat, SampleArgs* a) {
+    if (!planes || !grid) return fail(TT_E_ARG, "%s: planes/grid NULL", who);
+    if (N < 0 || K < 1 || K > SMP_MAXK || C < 4 || (C & 3) || H < 1 || W < 1 || M < 0)
+        return fail(TT_E_ARG, "%s: bad sizes (1 <= K <= 4, C a multiple of 4)", who);
+    if (!aligned16(planes)) return fail(TT_E_ALIGN, "%s: planes must be 16-byte aligned", who);
+    int seg = 1;
+    while (seg < (C >> 2) && seg < 32) seg <<= 1;
+    *a = SampleArgs{planes, grid, N, K, C, H, W, M, concat ? 1 : 0, seg};
+    return TT_OK;
+}
+static unsigned sample_grid_dim(const SampleArgs& a) { return (unsigned)(((int64_t)a.N * a.M * a.seg + 255) / 256); }
+
+int tt_sample_planes_fwd(const float* planes, int N, int K, int C, int H, int W, const float* grid, int64_t M, int concat,
+                         float* out, void* stream) {
+    SampleArgs a;
+    if (int e = sample_args("tt_sample_planes_fwd", planes, N, K, C, H, W, grid, M, concat, &a)) return e;
+    if (!out || !aligned16(out)) return fail(TT_E_ARG, "tt_sample_planes_fwd: out NULL or misaligned%s", "");
+    if ((int64_t)N * M == 0) return TT_OK;
+    switch (K) {
+        case 1: TT_LAUNCH(k_sample_fwd<1>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, out); break;
+        case 2: TT_LAUNCH(k_sample_fwd<2>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, out); break;
+        case 3: TT_LAUNCH(k_sample_fwd<3>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, out); break;
+        default: TT_LAUNCH(k_sample_fwd<4>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, out); break;
+    }
+    return check_launch("tt_sample_planes_fwd");
+}
+int tt_sample_planes_bwd(const float* planes, int N, int K, int C, int H, int W, const float* grid, int64_t M, int concat,
+                         const float* g_out, float* g_planes, float* g_grid, void* stream) {
+    SampleArgs a;
+    if (int e = sample_args("tt_sample_planes_bwd", planes, N, K, C, H, W, grid, M, concat, &a)) return e;
+    if (!g_out || !aligned16(g_out) || (g_planes && !aligned16(g_planes)))
+        return fail(TT_E_ARG, "tt_sample_planes_bwd: g_out NULL or misaligned pointer%s", "");
+    if ((int64_t)N * M == 0 || (!g_planes && !g_grid)) return TT_OK;
+    TT_LAUNCH(k_sample_bwd, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, g_out, g_planes, g_grid);
+    return check_launch("tt_sample_planes_bwd");
+}
+int tt_sample_planes_bwdbwd(const float* planes, int N, int K, int C, int H, int W, const float* grid, int64_t M, int concat,
+                            const float* g_out, const float* gg_planes, const float* gg_grid, float* gg_out,
+                            float* g_planes, float* g_grid, void* stream) {
+    SampleArgs a;
+    if (int e = sample_args("tt_sample_planes_bwdbwd", planes, N, K, C, H, W, grid, M, concat, &a)) return e;
+    if (!g_out || !aligned16(g_out) || (gg_planes && !aligned16(gg_planes)) || (gg_out && !aligned16(gg_out)) ||
+        (g_planes && !aligned16(g_planes)))
+        return fail(TT_E_ARG, "tt_sample_planes_bwdbwd: g_out NULL or misaligned pointer%s", "");
+    if ((int64_t)N * M == 0 || (!gg_out && !g_planes && !g_grid)) return TT_OK;
+    switch (K) {
+        case 1: TT_LAUNCH(k_sample_bwdbwd<1>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, g_out, gg_planes, gg_grid, gg_out, g_planes, g_grid); break;
+        case 2: TT_LAUNCH(k_sample_bwdbwd<2>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, g_out, gg_planes, gg_grid, gg_out, g_planes, g_grid); break;
+        case 3: TT_LAUNCH(k_sample_bwdbwd<3>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, g_out, gg_planes, gg_grid, gg_out, g_planes, g_grid); break;
+        default: TT_LAUNCH(k_sample_bwdbwd<4>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, g_out, gg_planes, gg_grid, gg_out, g_planes, g_grid); break;
+    }
+    return check_launch("tt_sample_planes_bwdbwd");
+}
+static int transpose_batched(const char* who, const float* src, int64_t B, int64_t rows, int64_t cols, float* dst, void* stream) {
+    if (!src || !dst) return fail(TT_E_ARG, "%s: NULL pointer", who);
+    if (B < 0 || rows < 1 || cols < 1 || B > 65535 || (rows + 31) / 32 > 65535) return fail(TT_E_ARG, "%s: bad sizes", who);
+    if (B == 0) return TT_OK;
+    TT_LAUNCH(k_transpose, dim3((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)B), 256, 0, (cudaStream_t)stream, src, dst, rows, cols);
+    return check_launch(who);
+}
+int tt_to_channel_last(const float* src, int64_t B, int C, int64_t HW, float* dst, void* stream) {
+    return transpose_batched("tt_to_channel_last", src, B, C, HW, dst, stream);
+}
+int tt_from_channel_last(const float* src, int64_t B, int C, int64_t HW, float* dst, void* stream) {
+    return transpose_batched("tt_from_channel_last", src, B, HW, C, dst, stream);
 }
 
 }  // extern "C"
