@@ -1118,6 +1118,7 @@ static int sample_args(const char* who, const float* planes, int N, int K, int C
     return TT_OK;
 }
 static unsigned sample_grid_dim(const SampleArgs& a) { return (unsigned)(((int64_t)a.N * a.M * a.seg + 255) / 256); }
+static unsigned sample_grid_flat(const SampleArgs& a) { return (unsigned)(((int64_t)a.N * a.M * (a.C >> 2) + 255) / 256); }
 
 int tt_sample_planes_fwd(const float* planes, int N, int K, int C, int H, int W, const float* grid, int64_t M, int concat,
                          float* out, void* stream) {
@@ -1126,10 +1127,10 @@ int tt_sample_planes_fwd(const float* planes, int N, int K, int C, int H, int W,
     if (!out || !aligned16(out)) return fail(TT_E_ARG, "tt_sample_planes_fwd: out NULL or misaligned%s", "");
     if ((int64_t)N * M == 0) return TT_OK;
     switch (K) {
-        case 1: TT_LAUNCH(k_sample_fwd<1>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, out); break;
-        case 2: TT_LAUNCH(k_sample_fwd<2>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, out); break;
-        case 3: TT_LAUNCH(k_sample_fwd<3>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, out); break;
-        default: TT_LAUNCH(k_sample_fwd<4>, sample_grid_dim(a), 256, 0, (cudaStream_t)stream, a, out); break;
+        case 1: TT_LAUNCH(k_sample_fwd<1>, sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
+        case 2: TT_LAUNCH(k_sample_fwd<2>, sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
+        case 3: TT_LAUNCH(k_sample_fwd<3>, sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
+        default: TT_LAUNCH(k_sample_fwd<4>, sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
     }
     return check_launch("tt_sample_planes_fwd");
 }

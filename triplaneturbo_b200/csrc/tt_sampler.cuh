@@ -56,11 +56,12 @@ struct SampleArgs {
 
 template <int K>
 __global__ void __launch_bounds__(256) k_sample_fwd(SampleArgs a, float* __restrict__ out) {
+    // the forward needs no reduction over the lanes of a point: items (point, chunk) are simply flattened over the threads
+    const int U = a.C >> 2, OS = a.concat ? K * a.C : a.C;
     const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int64_t pt = t / a.seg; const int l = (int)(t % a.seg);
+    const int64_t pt = t / U; const int ch = (int)(t - pt * U);
     if (pt >= (int64_t)a.N * a.M) return;
     const int64_t n = pt / a.M, m = pt - n * a.M;
-    const int U = a.C >> 2, OS = a.concat ? K * a.C : a.C;
     const size_t ps = (size_t)a.H * a.W * a.C;
     TapsHW tp[K];
 #pragma unroll
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) k_sample_fwd(SampleArgs a, float* __restr
         tp[k] = make_taps_hw(g[0], g[1], a.H, a.W);
     }
     float* orow = out + (size_t)pt * OS;
-    for (int ch = l; ch < U; ch += a.seg) {
+    {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
