@@ -32,5 +32,8 @@ Parity pinning status
   ``extern/grid_sample_gradfix/gridsample_cuda.cu:87-209``, CUDA only) is
   restated as a gather-based bilinear that autograd differentiates twice; it
   is pinned against ``F.grid_sample`` (value and first derivative) and against
-  fp64 ``gradgradcheck``.
+  fp64 ``gradgradcheck``.  In addition ``oracle/build_ref.py`` compiles the
+  reference's own extension (from the sources under ``/root/reference``, output
+  only in ``oracle/_ref/``) and ``tests/test_sampler.py`` runs its ``grad2_2d``
+  next to ``tt_sample_planes_bwdbwd`` on the GPU.
 """

@@ -134,3 +134,40 @@ def test_grid_sample_2d_api_and_large_random_property():
     lhs = sample_planes(a + b, gr, 3, False)
     rhs = sample_planes(a, gr, 3, False) + sample_planes(b, gr, 3, False)
     assert max_abs(lhs, rhs) < 1e-4
+
+
+@pytest.mark.gpu
+def test_second_derivative_against_the_reference_kernel():
+    """tt_sample_planes_bwdbwd vs the reference's own CUDA kernel (grid_sampler_2d_grad2_kernel,
+    extern/grid_sample_gradfix/gridsample_cuda.cu:27-210), built by oracle/build_ref.py into oracle/_ref/."""
+    import importlib.util
+    import os
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "gridsample_grad2_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/gridsample_grad2_ref.so not built (needs /root/reference at build time)")
+    spec = importlib.util.spec_from_file_location("gridsample_grad2_ref", so)
+    ref_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_mod)
+    from triplaneturbo_b200.ops import _lib, _ptr, _stream
+    from triplaneturbo_b200 import _cabi
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(21)
+    NK, C_, H, W, M = 3, 32, 16, 12, 4099
+    inp = torch.randn(NK, C_, H, W, generator=g).to(dev)
+    grid = ((torch.rand(NK, 1, M, 2, generator=g) * 2 - 1) * 1.1).to(dev)
+    go = torch.randn(NK, C_, 1, M, generator=g).to(dev)
+    ggI = torch.randn(NK, C_, H, W, generator=g).to(dev)
+    ggG = torch.randn(NK, 1, M, 2, generator=g).to(dev)
+    r_ggo, r_gi, r_gg = ref_mod.grad2_2d(ggI, ggG, go, inp, grid, False, False)      # padding zeros, align_corners False
+    cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    planes, ggp = cl(inp), cl(ggI)
+    go_pm = go[:, :, 0, :].permute(0, 2, 1).contiguous()                              # [NK, M, C]
+    e_ggo = torch.empty_like(go_pm); e_gp = torch.zeros_like(planes); e_gg = torch.empty(NK, M, 2, device=dev)
+    L = _lib()
+    _cabi.check(L, L.tt_sample_planes_bwdbwd(_ptr(planes), NK, 1, C_, H, W, _ptr(grid.reshape(NK, M, 2).contiguous()), M, 0,
+                                             _ptr(go_pm), _ptr(ggp), _ptr(ggG.reshape(NK, M, 2).contiguous()), _ptr(e_ggo),
+                                             _ptr(e_gp), _ptr(e_gg), _stream(torch.device(dev))), "bwdbwd")
+    torch.cuda.synchronize()
+    assert rel_err(e_ggo.permute(0, 2, 1).unsqueeze(2), r_ggo) < 1e-5
+    assert rel_err(e_gp.permute(0, 3, 1, 2), r_gi) < 1e-5
+    assert rel_err(e_gg.reshape(NK, 1, M, 2), r_gg) < 1e-5
