@@ -307,6 +307,9 @@ def main():
                 "hbm_compulsory_gbs": (planes_bytes * 2 + n_rays * 80) * args.steps / (ms_total * 1e-3) / 1e9,
                 # measured DRAM bytes of the dominant kernel / its live duration vs the measured HBM peak: the path is
                 # not HBM-bound (it is bound by the L1/L2 gather and reduction path)
+                # 3xTF32 (forward kernels) runs 3 TF32 MMAs per product and TF32 peaks at half the bf16 rate: the tensor
+                # pipe can deliver at most 1/6 of `peak` as algorithmic FLOPs (1/2 for the single-pass backward kernels)
+                "split_precision_ceiling": (1.0 / 6.0) if dom in ("k_geo_tc", "k_tex_tc") else 0.5,
                 "hbm_gbs_achieved": (traffic / (kern_ms[dom] * 1e-3) / 1e9) if traffic else None,
                 "hbm_peak_gbs": peaks.get("hbm_gbs"),
                 "kernels_ms": {k: round(v, 4) for k, v in kern_ms.items()},
