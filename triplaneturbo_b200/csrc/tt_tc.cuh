@@ -2,11 +2,13 @@
 // plus the light per-ray kernels around them.  See tt_umma.cuh for the execution model.
 //
 // Forward pipeline (tt_render_fwd, impl = 1):
-//   k_geo_tc<C,true>   sdf, d sdf/dx at every sample                     (tensor cores, cooperative gathers)
-//   k_weights          per ray: NeuS alpha, transmittance, weights, all non-colour accumulators, live-sample list
-//   k_tex_tc<C>        colour features at the live samples (T > 0)        (tensor cores)
-//   k_accum_rgb        per ray: Σ w · sigmoid_mipnerf(features)
-// Sampler (tt_importance_sample, impl = 1):  k_geo_tc<C,false> on the proposal midpoints, then k_sampler_post.
+//   k_classify         closed-form outputs of the empty samples, list of the others
+//   k_geo_tc<C,true>   sdf, d sdf/dx at every non-empty sample, ReLU masks  (tensor cores, cooperative gathers)
+//   k_weights          per ray: NeuS alpha, transmittance, weights, all non-colour accumulators, live-sample list (tt_rays.cuh)
+//   k_tex_tc<C>        colour features at the live samples (T > 0), ReLU masks (tensor cores)
+//   k_accum_rgb        per ray: Σ w · sigmoid_mipnerf(features)                  (tt_rays.cuh)
+// Sampler (tt_importance_sample, impl = 1):  k_classify + k_geo_tc<C,false> on the proposal midpoints, then k_sampler_post.
+// Field query (tt_geometry_fwd): k_geo_tc<C,false,DEFORM> also runs the deformation decoder on the same encoding.
 #pragma once
 #include "tt_device.cuh"
 #include "tt_umma.cuh"

@@ -1,15 +1,16 @@
-// Tensor-core (tcgen05) kernels of the backward path.  One group of 128 threads per CTA (thread = sample point =
-// TMEM lane), persistent over 128-point tiles.
+// Tensor-core (tcgen05) kernels of the backward path.  Two independent groups of 128 threads per CTA (thread = sample
+// point = TMEM lane) share the weight tiles; persistent over 128-point tiles of the compacted backward lists.
 //
-// Every matrix product of the backward runs on the tensor cores:
-//   * decoder recompute: 3xTF32 (SDF branch: the ReLU masks must equal the forward's) / 1xTF32 (colour branch),
-//   * adjoint / tangent layers: 1xTF32 (gradient precision), A operand in TMEM,
+// Nothing of the decoders is recomputed beyond what a gradient needs: the forward saved the ReLU masks of both decoders.
+//   * adjoint / tangent layers: single-pass TF32 (gradient precision), A operand in TMEM,
 //   * weight gradients dW = Σ_points a ⊗ x: both operands written by the threads into K-major shared-memory tiles
 //     (K = the tile's 128 points), accumulated in TMEM across all tiles of the CTA and flushed once with atomicAdd.
-//     The MMA shape is M = 128: only the first 64 (or 3) rows of A are meaningful, the remaining rows read whatever
-//     follows in shared memory and land in accumulator rows that are never read.
+//     The MMA shape is M = 128: only the first 64 rows of A are meaningful, the remaining rows read the B tile behind it
+//     and land in accumulator rows that are never read.
+//   * SDF branch: dW2 and dw3 both come out of one accumulator Q = Σ m2 ⊗ h̃1 (k_bwd_geo_tc),
+//   * colour branch: first-layer gradients through hidden-gradient planes (k_bwd_tex_tc, k_hid_planes, k_hid_wgrad).
 // Plane gradients: cooperative scatter (consecutive lanes = consecutive 16-byte chunks of one texel) with
-// red.global.add.v4.f32.
+// red.global.add.v4.f32; run-length merged over consecutive samples for the 64-wide colour scatter.
 #pragma once
 #include "tt_tc.cuh"
 
