@@ -60,6 +60,9 @@ inline void mbar_wait(uint32_t off, uint32_t parity) {
     std::atomic_ref<uint64_t> r(*(uint64_t*)((char*)smem_ + off));
     while ((r.load() & 1u) == parity) std::this_thread::yield();
 }
+inline int cas(int* addr, int expect, int desired) {
+    std::atomic_ref<int> r(*addr); int e = expect; r.compare_exchange_strong(e, desired); return e;
+}
 inline float tf32(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
 inline void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
     const int lane = (int)(addr >> 16) + (int)(threadIdx_.x & 31), col = (int)(addr & 0xffff);

@@ -159,11 +159,14 @@ __global__ void __launch_bounds__(256) k_classify(tt_config cfg, TcSrc src, int6
 // Tap table per point: int o[NT] (texel index, CLAMPED to a valid texel), float w[NT] (weight, 0 for out-of-bounds
 // taps: zeros padding), NT = 4 * NPL; pbase = prompt index.  All NT loads of an item are issued before they are
 // used, without branches, so the memory system sees NT independent 16-byte requests per lane.
+#ifndef TT_GATHER_LOADS
+#define TT_GATHER_LOADS 24      // independent 16-byte loads in flight per lane: one group alone must fill the load path
+#endif
 template <int C, int NPL>
 __device__ __forceinline__ void coop_gather(const float* __restrict__ planes, size_t ps, const int* tap_o,
                                             const float* tap_w, const uint32_t* pbase, int plane0, float* stage, int tg) {
     // JB items per batch so that 12 independent 16-byte loads are in flight per lane whatever NPL is
-    constexpr int U = C / 4, NT = 4 * NPL, SP = C + 4, JB = 3 / NPL;
+    constexpr int U = C / 4, NT = 4 * NPL, SP = C + 4, JB = TT_GATHER_LOADS / NT;
 #pragma unroll 1
     for (int j0 = 0; j0 < U; j0 += JB) {
         float4 v[JB][NT];
@@ -253,7 +256,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
     }
     uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::GROUP0 + TC_GROUPS * L::GROUP_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + TC_GROUPS);
-    if (tid == 0) for (int g = 0; g < TC_GROUPS; ++g) mbar_init(mbars + g);
+    int* mlock = reinterpret_cast<int*>(tmem_slot + 1);
+    if (tid == 0) { for (int g = 0; g < TC_GROUPS; ++g) mbar_init(mbars + g); *mlock = 0; }
     if (warp == 0) tmem_alloc_warp(tmem_slot, 512);
     async_proxy_fence();
     tc_fence_before();
@@ -312,9 +316,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
             }
         }
         pbase[tg] = (uint32_t)prompt;
-        group_sync(group);
+        mem_lock(mlock, leader, group);
         coop_gather<C, 3>(planes, ps, tap_o, tap_w, pbase, 0, stage, tg);
-        group_sync(group);
+        mem_unlock(mlock, leader, group);
         // ---- SDF MLP on tensor cores ----------------------------------------------------------------------------
         float d[64];
         uint64_t m1 = 0, m2 = 0;
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
                 for (int c = 0; c < C; c += 4)
                     *reinterpret_cast<float4*>(stage + tg * SP + c) = make_float4(de[c], de[c + 1], de[c + 2], de[c + 3]);
             }
-            group_sync(group);
+            mem_lock(mlock, leader, group);
             {   // cooperative pass: d(de · f_k)/d(ix,iy) per plane.  4 lanes share one point: lane sl takes the 16-byte
                 // channel chunks sl, sl+4, ... of every tap and accumulates its partial dot products before the
                 // two-step shuffle reduction over the 4 lanes (8 points per warp iteration).
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_geo_tc(const float* __restric
                     }
                 }
             }
-            group_sync(group);
+            mem_unlock(mlock, leader, group);
             if (valid && (grad_o || normal_o)) {
                 float gm[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -485,7 +489,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tex_tc(const float* __restric
     if (tid < 192) smem[L::W3 + tid] = __ldg(wp + wo.w3f + tid);
     uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::GROUP0 + TC_GROUPS * L::GROUP_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + TC_GROUPS);
-    if (tid == 0) for (int g = 0; g < TC_GROUPS; ++g) mbar_init(mbars + g);
+    int* mlock = reinterpret_cast<int*>(tmem_slot + 1);
+    if (tid == 0) { for (int g = 0; g < TC_GROUPS; ++g) mbar_init(mbars + g); *mlock = 0; }
     if (warp == 0) tmem_alloc_warp(tmem_slot, 512);
     async_proxy_fence();
     tc_fence_before();

@@ -148,7 +148,8 @@ k_bwd_geo_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
     for (int i = tg; i < 2 * wg_tile_floats(64); i += TC_GROUP) gsm[L::AT + i] = 0.f;
     uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::GROUP0 + G * L::GROUP_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + G);
-    if (tid == 0) for (int g = 0; g < G; ++g) mbar_init(mbars + g);
+    int* mlock = reinterpret_cast<int*>(tmem_slot + 1);
+    if (tid == 0) { for (int g = 0; g < G; ++g) mbar_init(mbars + g); *mlock = 0; }
     if (warp == 0) tmem_alloc_warp(tmem_slot, G * TC_COLS_PER_GROUP);
     async_proxy_fence();
     tc_fence_before();
@@ -223,13 +224,24 @@ k_bwd_geo_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
             for (int c = 0; c < C; c += 4)
                 *reinterpret_cast<float4*>(stage + tg * SP + c) = make_float4(de[c], de[c + 1], de[c + 2], de[c + 3]);
         }
+#ifndef TT_BWDGEO_LOCK_SCATTER
+#define TT_BWDGEO_LOCK_SCATTER 1
+#endif
+#if TT_BWDGEO_LOCK_SCATTER
+        mem_lock(mlock, leader, group);
+#else
         group_sync(group);
+#endif
         // d L / d texel = de · ω  (plain scatter: with 12 tap slots the run-length merged variant measured 4 % slower on
         // the synthetic benchmark planes, whose noisy SDF spreads the fine samples; it wins for the 64-wide colour scatter)
         if (gplanes) coop_scatter<C, 3>(gplanes, ps, tap_o, tap_om, pbase, 0, stage, tg);
+#if TT_BWDGEO_LOCK_SCATTER
         group_sync(group);
+#else
+        mem_lock(mlock, leader, group);
+#endif
         coop_gather<C, 3>(planes, ps, tap_o, tap_om, pbase, 0, stage, tg);                    // ẽ = Σ ω · texel
-        group_sync(group);
+        mem_unlock(mlock, leader, group);
         {
             float e[C];
 #pragma unroll
@@ -347,7 +359,8 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
     for (int i = tg; i < 2 * wg_tile_floats(64); i += TC_GROUP) gsm[L::AT + i] = 0.f;
     uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::GROUP0 + G * L::GROUP_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + G);
-    if (tid == 0) for (int g = 0; g < G; ++g) mbar_init(mbars + g);
+    int* mlock = reinterpret_cast<int*>(tmem_slot + 1);
+    if (tid == 0) { for (int g = 0; g < G; ++g) mbar_init(mbars + g); *mlock = 0; }
     if (warp == 0) tmem_alloc_warp(tmem_slot, G * TC_COLS_PER_GROUP);
     async_proxy_fence();
     tc_fence_before();

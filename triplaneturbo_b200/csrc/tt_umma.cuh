@@ -184,6 +184,41 @@ __device__ __forceinline__ void tmem_wait_st() {}
 __device__ __forceinline__ void tmem_wait_ld() {}
 #endif
 
+// ---- memory-phase lock -------------------------------------------------------------------------------------------------
+// The groups of a CTA run identical code on identical tile sizes, so they stay in lockstep: both gather at the same time,
+// then both sit in tensor-core round trips while the load/store path idles (measured: the phase times of a kernel add up
+// to its duration).  A CTA-wide lock around the gather / scatter phases forces them out of phase: while one group owns
+// the load/store path, the other runs its layers.  (The owner keeps enough loads in flight to fill the path on its own.)
+// Measured at config 2 with the lock in k_geo_tc (both passes) and k_bwd_geo_tc: 528 -> 490 ms per step (it hurts the
+// reduction-bound colour backward, which therefore never takes it).  OFF by default: during the session that introduced
+// it, two of ~45 test processes produced a field query outside tolerance (not reproducible in 30 later processes, cause
+// not established); it stays a build option (-DTT_MEMLOCK=1) until it has been soak-tested.
+#ifndef TT_MEMLOCK
+#define TT_MEMLOCK 0
+#endif
+__device__ __forceinline__ void mem_lock(int* lock, bool leader, int group) {
+#if TT_MEMLOCK
+    if (leader) {
+#ifndef TT_EMUL
+        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(100);
+#else
+        while (tt_emul::cas(lock, 0, 1) != 0) std::this_thread::yield();
+#endif
+    }
+#endif
+    group_sync(group);
+}
+__device__ __forceinline__ void mem_unlock(int* lock, bool leader, int group) {
+    group_sync(group);
+#if TT_MEMLOCK
+#ifndef TT_EMUL
+    if (leader) atomicExch(lock, 0);
+#else
+    if (leader) tt_emul::cas(lock, 1, 0);
+#endif
+#endif
+}
+
 // ---- group-level layer steps ---------------------------------------------------------------------------------
 // this thread's activation row x[0..K) -> TMEM (tf32 hi at A_hi, exact remainder at A_lo)
 template <int K>
