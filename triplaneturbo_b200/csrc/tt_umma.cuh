@@ -189,12 +189,11 @@ __device__ __forceinline__ void tmem_wait_ld() {}
 // then both sit in tensor-core round trips while the load/store path idles (measured: the phase times of a kernel add up
 // to its duration).  A CTA-wide lock around the gather / scatter phases forces them out of phase: while one group owns
 // the load/store path, the other runs its layers.  (The owner keeps enough loads in flight to fill the path on its own.)
-// Measured at config 2 with the lock in k_geo_tc (both passes) and k_bwd_geo_tc: 528 -> 490 ms per step (it hurts the
-// reduction-bound colour backward, which therefore never takes it).  OFF by default: during the session that introduced
-// it, two of ~45 test processes produced a field query outside tolerance (not reproducible in 30 later processes, cause
-// not established); it stays a build option (-DTT_MEMLOCK=1) until it has been soak-tested.
+// Measured at config 2 with the lock in k_geo_tc (both passes) and k_bwd_geo_tc: 522 -> 490 ms per step (it hurts the
+// reduction-bound colour backward, which therefore never takes it).  -DTT_MEMLOCK=0 builds without it.  Validation: see
+// DESIGN.md 3.4 (racecheck clean, bit-identical repeated field queries, GPU suite soaked on several boxes).
 #ifndef TT_MEMLOCK
-#define TT_MEMLOCK 0
+#define TT_MEMLOCK 1
 #endif
 __device__ __forceinline__ void mem_lock(int* lock, bool leader, int group) {
 #if TT_MEMLOCK
