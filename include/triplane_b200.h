@@ -124,6 +124,17 @@ int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cf
                     const float* g_sdf, const float* g_features, const float* g_normal,
                     const float* g_sdf_grad, float* scratch, float* gplanes, float* gw, void* stream);
 
+/* Backward of the field query of the mesh paths: forward_field = sdf + deformation decoders on one geometry
+ * encoding (few_step…diffusion.py:375-394, trained through at
+ * custom/triplaneturbo/models/renderers/generative_space_mesh_rasterize_renderer.py:449-452).
+ * g_sdf [N], g_deformation [N][3] (nullable).  gplanes and gw (tt_wgrad_floats, sdf blocks) are ACCUMULATED into;
+ * gw_def (tt_wgrad_def_floats: [64][C] | [64][64] | [3][64], nn.Linear layout) likewise.
+ * scratch: tt_geometry_bwd_scratch_floats(cfg, P*M) floats. */
+size_t tt_wgrad_def_floats(int C);
+int tt_field_bwd(const float* planes, const float* wpack, const tt_config* cfg,
+                 const float* points, int64_t M, const float* g_sdf, const float* g_deformation,
+                 float* scratch, float* gplanes, float* gw, float* gw_def, void* stream);
+
 /* ---- importance sampling ---------------------------------------------------------------
  * Replaces: ImportanceEstimator.sampling (threestudio/models/estimators.py:22-101) with the
  * proposal closure of the renderer (…sdf_volume_renderer.py:243-316) and the two

@@ -51,10 +51,16 @@ inline float tmem_[128][512];
 // ---- tcgen05 emulation (see triplaneturbo_b200/csrc/tt_umma.cuh) ------------------------------------------
 inline uint32_t smem_off(const void* p) { return (uint32_t)((const char*)p - (const char*)smem_); }
 inline void group_sync(int g) { gbar_[g]->arrive_and_wait(); }
-inline void mbar_init(uint64_t* bar) { *bar = 0; }
+// mbarrier: bits [0,20) completed phases, [20,40) arrivals of the current phase, [40,60) expected arrivals per phase
+inline void mbar_init(uint64_t* bar, uint32_t count = 1) { *bar = (uint64_t)count << 40; }
 inline void mbar_arrive(uint32_t off) {
     std::atomic_ref<uint64_t> r(*(uint64_t*)((char*)smem_ + off));
-    r.fetch_add(1);
+    uint64_t old = r.load();
+    for (;;) {
+        const uint64_t expect = old >> 40, arr = ((old >> 20) & 0xfffff) + 1, ph = old & 0xfffff;
+        const uint64_t nw = arr >= expect ? ((expect << 40) | ((ph + 1) & 0xfffff)) : ((expect << 40) | (arr << 20) | ph);
+        if (r.compare_exchange_weak(old, nw)) break;
+    }
 }
 inline void mbar_wait(uint32_t off, uint32_t parity) {
     std::atomic_ref<uint64_t> r(*(uint64_t*)((char*)smem_ + off));
@@ -72,8 +78,9 @@ inline void tmem_ld8(uint32_t addr, uint32_t (&v)[8]) {
     const int lane = (int)(addr >> 16) + (int)(threadIdx_.x & 31), col = (int)(addr & 0xffff);
     for (int j = 0; j < 8; ++j) std::memcpy(&v[j], &tmem_[lane][col + j], 4);
 }
-// D[128][N] (+)= A[128][K] * B[N][K]^T ; A hi at col a0, lo at col 64+a0, D at col 128 of the group's region
-inline void umma(uint32_t tmem, uint32_t a_col0, uint32_t bhi, uint32_t blo, uint32_t sbo, int N, int K, bool acc, int passes) {
+// D[128][N] (+)= A[128][K] * B[N][K]^T ; A hi / lo / D at explicit columns of the group's region
+inline void umma_ex(uint32_t tmem, uint32_t col_hi, uint32_t col_lo, uint32_t col_d, uint32_t bhi, uint32_t blo, uint32_t sbo,
+                    int N, int K, bool acc, int passes) {
     const int c0 = (int)(tmem & 0xffff);
     auto B = [&](uint32_t base, int n, int k) {
         const uint32_t off = base + (n & 7) * 16 + (n >> 3) * sbo + (k >> 2) * 128 + (k & 3) * 4;
@@ -81,18 +88,21 @@ inline void umma(uint32_t tmem, uint32_t a_col0, uint32_t bhi, uint32_t blo, uin
     };
     for (int m = 0; m < 128; ++m)
         for (int n = 0; n < N; ++n) {
-            float d = acc ? tmem_[m][c0 + 128 + n] : 0.f;
+            float d = acc ? tmem_[m][c0 + col_d + n] : 0.f;
             for (int k0 = 0; k0 < K; k0 += 8) {
                 float s1 = 0.f, s2 = 0.f, s3 = 0.f;
                 for (int k = k0; k < k0 + 8; ++k) {
-                    const float ah = tf32(tmem_[m][c0 + a_col0 + k]), al = tf32(tmem_[m][c0 + 64 + a_col0 + k]);
+                    const float ah = tf32(tmem_[m][c0 + col_hi + k]);
                     s3 += ah * B(bhi, n, k);
-                    if (passes == 3) { s1 += al * B(bhi, n, k); s2 += ah * B(blo, n, k); }
+                    if (passes == 3) { const float al = tf32(tmem_[m][c0 + col_lo + k]); s1 += al * B(bhi, n, k); s2 += ah * B(blo, n, k); }
                 }
                 d = ((d + s1) + s2) + s3;
             }
-            tmem_[m][c0 + 128 + n] = d;
+            tmem_[m][c0 + col_d + n] = d;
         }
+}
+inline void umma(uint32_t tmem, uint32_t a_col0, uint32_t bhi, uint32_t blo, uint32_t sbo, int N, int K, bool acc, int passes) {
+    umma_ex(tmem, a_col0, 64 + a_col0, 128, bhi, blo, sbo, N, K, acc, passes);
 }
 // G[128][N] (+)= At * Bt^T over 128 points; operand tiles with LBO 144 / SBO 4608 (tt_umma.cuh wg_off)
 inline void umma_ss(uint32_t d_addr, uint32_t a, uint32_t b, int N, bool acc) {

@@ -110,6 +110,22 @@ class Emul:
                                        ptr(scratch), ptr(gplanes), ptr(gw), None), "geometry_bwd")
         return gplanes, self.split_wgrad(gw, cfg.C)
 
+    def field_bwd(self, planes, wp, cfg, points, g_sdf=None, g_def=None):
+        pts = f32(points)
+        M = pts.shape[1]
+        N = cfg.P * M
+        scratch = np.zeros(self.L.tt_geometry_bwd_scratch_floats(C.byref(cfg), N), np.float32)
+        gplanes = aligned_zeros(planes.shape)
+        gw = aligned_zeros(self.L.tt_wgrad_floats(cfg.C))
+        gwd = aligned_zeros(self.L.tt_wgrad_def_floats(cfg.C))
+        a = [None if x is None else f32(x) for x in (g_sdf, g_def)]
+        self.ok(self.L.tt_field_bwd(ptr(planes), ptr(wp), C.byref(cfg), ptr(pts), M, ptr(a[0]), ptr(a[1]), ptr(scratch),
+                                    ptr(gplanes), ptr(gw), ptr(gwd), None), "field_bwd")
+        Cc = cfg.C
+        gd = [gwd[:64 * Cc].reshape(64, Cc).copy(), gwd[64 * Cc:64 * Cc + 4096].reshape(64, 64).copy(),
+              gwd[64 * Cc + 4096:].reshape(3, 64).copy()]
+        return gplanes, self.split_wgrad(gw, Cc)[:3], gd
+
     def split_wgrad(self, gw, C_):
         off = (C.c_int64 * 6)()
         self.ok(self.L.tt_wgrad_offsets(C_, off), "wgrad_offsets")

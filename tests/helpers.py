@@ -85,28 +85,6 @@ def random_decoder(*a, **k):
     return f(*a, **k)
 
 
-def build_plugins(fx, device, n_samples=64, n_imp=128, normal_direction="camera", rgb_grad_shrink=1.0):
-    """Geometry + renderer plugins (by registry name, like the reference's systems do) holding a fixture's weights."""
-    import triplaneturbo_b200 as tt
-    C_ = fx["space_cache"].shape[2]
-    geom = tt.find("few-step-triplane-dual-stable-diffusion")(dict(
-        radius=1.0, normal_type="analytic", sdf_bias="sphere", sdf_bias_params=0.5, rotate_planes="v1",
-        split_channels="v1", geo_interpolate="v1", tex_interpolate="v2",
-        space_generator_config={"output_dim": 2 * C_}, isosurface_deformable_grid=True)).to(device)
-    sd = {}
-    for name in ("sdf", "feature", "deformation"):
-        for i, idx in enumerate((0, 2, 4)):
-            if f"w_{name}_{i}" in fx:
-                sd[f"{name}_network.layers.{idx}.weight"] = fx[f"w_{name}_{i}"]
-    missing = geom.load_state_dict(sd, strict=False)
-    assert not missing.unexpected_keys
-    material = tt.find("no-material")(dict(n_output_dims=3, color_activation="sigmoid-mipnerf", requires_normal=True))
-    background = tt.find("solid-color-background")({}).to(device)
-    rend = tt.find("generative-space-sdf-volume-renderer")(dict(
-        radius=1.0, use_volsdf=False, trainable_variance=False, learned_variance_init=0.4605,
-        rgb_grad_shrink=rgb_grad_shrink, estimator="importance", num_samples_per_ray=n_samples,
-        num_samples_per_ray_importance=n_imp, near_plane=0.1, far_plane=4.0, train_chunk_size=0, randomized=False,
-        normal_direction=normal_direction, eval_chunk_size=500), geometry=geom, material=material,
-        background=background).to(device)
-    rend.update_step(0, 0)
-    return geom, rend
+def build_plugins(*a, **k):
+    from triplaneturbo_b200.synthetic import build_plugins as f
+    return f(*a, **k)

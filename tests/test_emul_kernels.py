@@ -16,7 +16,7 @@ TOL = 1e-4      # north_star: 1e-4 on RGB / sigma
 GTOL = 2e-3     # gradients, relative to the tensor's max magnitude
 
 
-@pytest.fixture(scope="module", params=[1, 0], ids=["tcgen05", "simt"])
+@pytest.fixture(scope="module", params=[2, 1, 0], ids=["tcgen05-ws", "tcgen05-r1", "simt"])
 def em(request):
     e = Emul()
     e.set_impl(request.param)     # both kernel families run through the same checks
@@ -75,6 +75,32 @@ def test_geometry_backward(em, name):
     names = [f"grad_w_sdf_{i}" for i in range(3)] + [f"grad_w_feature_{i}" for i in range(3)]
     for n, g in zip(names, gw):
         assert rel_err(torch.from_numpy(g), fx[n]) < GTOL, n
+
+
+@pytest.mark.parametrize("name", ["geometry_c8_r16", "geometry_c32_r16"])
+def test_field_backward_with_deformation(em, name):
+    """forward_field (sdf + deformation) is differentiable w.r.t. planes, the SDF decoder and the deformation decoder
+    (few_step…diffusion.py:375-394; the mesh renderer trains through it): tt_field_bwd vs autograd of the oracle."""
+    fx = load_golden(name)
+    w = weights_from(fx)
+    P, _, C_, R, _ = fx["space_cache"].shape
+    cfg = em.config(C_, R, P)
+    planes = em.repack(fx["space_cache"].numpy())
+    wp = em.pack_weights(np_w(w), C_)
+    g = torch.Generator().manual_seed(11)
+    M = fx["points"].shape[1]
+    cot_s, cot_d = torch.randn(P, M, 1, generator=g), torch.randn(P, M, 3, generator=g)
+    sc = fx["space_cache"].clone().requires_grad_(True)
+    wr = {k: [t.clone().requires_grad_(True) for t in v] for k, v in w.items()}
+    sdf, deform = rp.forward_field(fx["points"], sc, wr, rp.PathConfig())
+    loss = (sdf * cot_s).sum() + (deform * cot_d).sum()
+    want = torch.autograd.grad(loss, [sc] + wr["sdf"] + wr["deformation"])
+    gplanes, gws, gwd = em.field_bwd(planes, wp, cfg, fx["points"].numpy(), g_sdf=cot_s.numpy().ravel(),
+                                     g_def=cot_d.numpy().reshape(-1, 3))
+    assert rel_err(torch.from_numpy(em.repack_bwd(gplanes)), want[0]) < GTOL
+    for i in range(3):
+        assert rel_err(torch.from_numpy(gws[i]), want[1 + i]) < GTOL, f"sdf {i}"
+        assert rel_err(torch.from_numpy(gwd[i]), want[4 + i]) < GTOL, f"deformation {i}"
 
 
 def test_isosurface_grid_points(em):

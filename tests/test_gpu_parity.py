@@ -16,12 +16,12 @@ from tests.helpers import (load_golden, weights_from, max_abs, rel_err, proposal
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[1, 0], ids=["tcgen05", "simt"])
+@pytest.fixture(autouse=True, params=[2, 1, 0], ids=["tcgen05-ws", "tcgen05-r1", "simt"])
 def kernel_family(request):
     """Every parity test runs on both kernel families: tcgen05 tensor-core kernels and the SIMT reference kernels."""
     ops.set_impl(request.param)
     yield request.param
-    ops.set_impl(1)
+    ops.set_impl(2)
 
 
 TOL = 1e-4

@@ -44,6 +44,8 @@ SIGNATURES = {
     "tt_geometry_fwd": (C.c_int, [fp, fp, _cfgp, fp, i64, C.c_int] + [fp] * 6 + [fp]),
     "tt_geometry_bwd_scratch_floats": (C.c_size_t, [_cfgp, i64]),
     "tt_geometry_bwd": (C.c_int, [fp, fp, _cfgp, fp, i64] + [fp] * 4 + [fp, fp, fp, fp]),
+    "tt_wgrad_def_floats": (C.c_size_t, [C.c_int]),
+    "tt_field_bwd": (C.c_int, [fp, fp, _cfgp, fp, i64, fp, fp, fp, fp, fp, fp, fp]),
     "tt_sample_scratch_floats": (C.c_size_t, [i64, C.c_int]),
     "tt_importance_sample": (C.c_int, [fp, fp, _cfgp, fp, fp, i64, C.c_int, C.c_int, fp, fp, fp, fp, fp]),
     "tt_render_fwd_scratch_floats": (C.c_size_t, [i64, C.c_int]),

@@ -3,6 +3,7 @@
 #include "tt_device.cuh"
 #include "tt_tc.cuh"
 #include "tt_tc_bwd.cuh"
+#include "tt_ws.cuh"
 #include "tt_rays.cuh"
 #include "tt_sampler.cuh"
 
@@ -16,7 +17,8 @@ using namespace tt;
 // host-side helpers
 // =====================================================================================================
 static thread_local char g_err[512] = "";
-static int g_impl = 1;      // 1: tcgen05 tensor-core kernels (tt_tc.cuh), 0: SIMT reference kernels (this file)
+static int g_impl = 2;      // 2: warp-specialised tcgen05 kernels (tt_ws.cuh; default), 1: round-1 tcgen05 kernels
+                            // (tt_tc.cuh), 0: SIMT reference kernels (this file)
 static const size_t kMaxSmem = 227 * 1024;
 static std::atomic<int64_t> g_launches{0};
 
@@ -95,6 +97,42 @@ static unsigned tc_grid(int64_t n_points) {
     const int64_t ctas = (n_points + TC_THREADS - 1) / TC_THREADS;
     return (unsigned)(ctas < (int64_t)num_sms() ? (ctas < 1 ? 1 : ctas) : num_sms());
 }
+// SDF decoder on a point list: warp-specialised kernel (impl 2) or the round-1 kernel (impl 1)
+template <int kC, bool NORMAL>
+static int launch_geo_decoder(const float* planes, const float* wpack, const tt_config* cfg, const TcSrc& src, int64_t N,
+                              float* sdf, float* sdf_orig, float* grad, float* normal, uint64_t* masks, cudaStream_t st) {
+    const size_t smw = (size_t)GeoWs<kC, NORMAL>::TOTAL * 4;
+    if (g_impl == 2 && smw <= kMaxSmem) {
+        if (int e = set_smem(k_geo_ws<kC, NORMAL>, smw)) return e;
+        const int64_t tiles = (N + TC_GROUP - 1) / TC_GROUP;
+        const unsigned grid = (unsigned)(tiles < (int64_t)num_sms() ? (tiles < 1 ? 1 : tiles) : num_sms());
+        TT_LAUNCH((k_geo_ws<kC, NORMAL>), grid, WS_THREADS, smw, st, planes, wpack, *cfg, src, N, sdf, sdf_orig, grad, normal, masks);
+        return check_launch("k_geo_ws");
+    }
+    const size_t smg = (size_t)GeoSmem<kC, NORMAL>::TOTAL * 4;
+    if (int e = set_smem(k_geo_tc<kC, NORMAL>, smg)) return e;
+    TT_LAUNCH((k_geo_tc<kC, NORMAL>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, src, N, sdf, sdf_orig, grad, normal, masks, (float*)nullptr);
+    return check_launch("k_geo_tc");
+}
+
+// colour decoder on a point list
+template <int kC>
+static int launch_tex_decoder(const float* planes, const float* wpack, const tt_config* cfg, const TcSrc& src, int64_t N,
+                              float* features, uint64_t* masks, cudaStream_t st) {
+    const size_t smw = (size_t)TexWs<kC>::TOTAL * 4;
+    if (g_impl == 2 && smw <= kMaxSmem) {
+        if (int e = set_smem(k_tex_ws<kC>, smw)) return e;
+        const int64_t tiles = (N + TC_GROUP - 1) / TC_GROUP;
+        const unsigned grid = (unsigned)(tiles < (int64_t)num_sms() ? (tiles < 1 ? 1 : tiles) : num_sms());
+        TT_LAUNCH(k_tex_ws<kC>, grid, WS_THREADS, smw, st, planes, wpack, *cfg, src, N, features, masks);
+        return check_launch("k_tex_ws");
+    }
+    const size_t smt = (size_t)TexSmem<kC>::TOTAL * 4;
+    if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
+    TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, src, N, features, masks);
+    return check_launch("k_tex_tc");
+}
+
 static inline size_t slab_bytes(int rows) { return (size_t)rows * ST * sizeof(float); }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 
@@ -622,6 +660,81 @@ __global__ void __launch_bounds__(TPB) k_bwd_tex(const float* __restrict__ plane
 }
 
 // =====================================================================================================
+// backward of the deformation decoder of forward_field (few_step…diffusion.py:375-394): same geometry encoding
+// (three planes summed), head [3][64], seed gd[3] per point.  One thread per point, fp32.
+// gwd: [64][C] | [64][64] | [3][64]  (nn.Linear layout, tt_wgrad_def_floats)
+// =====================================================================================================
+template <int C>
+__global__ void __launch_bounds__(TPB) k_bwd_def(const float* __restrict__ planes, const float* __restrict__ wp,
+                                                tt_config cfg, PtSrc src, int64_t N, const float* __restrict__ gd_i,
+                                                float* __restrict__ gplanes, float* __restrict__ gwd) {
+    TT_SHARED(smem);
+    float* sX = smem;                       // C rows: geometry encoding -> W1dᵀ g_h1
+    float* sA = sX + C * ST;                // 64 rows: h1
+    float* sB = sA + HID * ST;              // 64 rows: h2 -> g_h2 -> g_h1
+    float* sG = sB + HID * ST;              // 4 rows: gd
+    const int tid = threadIdx.x;
+    const WOff wo = woff(C);
+    const int64_t idx = (int64_t)blockIdx.x * TPB + tid;
+    float gd[3] = {0.f, 0.f, 0.f};
+    bool active = idx < N;
+    if (active) {
+        gd[0] = gd_i[idx * 3]; gd[1] = gd_i[idx * 3 + 1]; gd[2] = gd_i[idx * 3 + 2];
+        active = (gd[0] != 0.f) || (gd[1] != 0.f) || (gd[2] != 0.f);
+    }
+    if (!__syncthreads_or(active)) return;
+    const size_t ps = (size_t)cfg.R * cfg.R * C;
+    const float* geo = planes; float* ggeo = gplanes;
+    PointTaps pt; uint64_t m1 = 0, m2 = 0;
+    if (active) {
+        float x[3], p[3]; int prompt;
+        point_of(src, idx, x, prompt);
+        geo = planes + (size_t)prompt * 6 * ps; ggeo = gplanes + (size_t)prompt * 6 * ps;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
+        Taps tp[3];
+        point_taps(p, cfg.R, pt, tp);
+        gather<C, 3>(geo, ps, pt.o, pt.w, sX + tid);
+        float acc[HID];
+        zero64(acc); layer64_acc(acc, wp + wo.w1dT, C, sX + tid); m1 = store_relu64(acc, sA + tid);
+        zero64(acc); layer64_acc(acc, wp + wo.w2dT, HID, sA + tid); m2 = store_relu64(acc, sB + tid);
+    } else {
+        zero_col(sX + tid, C); zero_col(sA + tid, HID); zero_col(sB + tid, HID);
+    }
+    sG[tid] = gd[0]; sG[ST + tid] = gd[1]; sG[2 * ST + tid] = gd[2]; sG[3 * ST + tid] = 0.f;
+    __syncthreads();
+    if (gwd) wgrad(gwd + 64 * C + 4096, HID, sG, 3, sB, HID);          // dW3 += gd h2ᵀ
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
+            const float v = gd[0] * __ldg(wp + wo.w3d + j) + gd[1] * __ldg(wp + wo.w3d + HID + j) +
+                            gd[2] * __ldg(wp + wo.w3d + 2 * HID + j);
+            sB[j * ST + tid] = ((m2 >> j) & 1ull) ? v : 0.f;           // g_h2
+        }
+    }
+    __syncthreads();
+    if (gwd) wgrad(gwd + 64 * C, HID, sB, HID, sA, HID);               // dW2 += g_h2 h1ᵀ
+    __syncthreads();
+    if (active) {
+        float acc[HID];
+        zero64(acc); layerT_acc<HID>(acc, wp + wo.w2d, HID, sB + tid); store_masked64(acc, m1, sB + tid);   // g_h1
+    }
+    __syncthreads();
+    if (gwd) wgrad(gwd, C, sB, HID, sX, C);                            // dW1 += g_h1 eᵀ
+    __syncthreads();
+    if (active && gplanes) {
+        float ge[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) ge[c] = 0.f;
+        layerT_acc<C>(ge, wp + wo.w1d, C, sB + tid);
+#pragma unroll
+        for (int c = 0; c < C; ++c) sX[c * ST + tid] = ge[c];
+        scatter_col<C, 3>(ggeo, ps, pt.o, pt.w, sX + tid);
+    }
+}
+
+// =====================================================================================================
 // stand-alone compositor (nerfacc.render_weight_from_alpha + accumulate_along_rays, dense rays)
 // =====================================================================================================
 __global__ void k_composite_fwd(const float* __restrict__ alphas, const float* __restrict__ values, int64_t n_rays,
@@ -703,7 +816,7 @@ int tt_profile_end(char* buf, size_t cap) {
     return TT_OK;
 }
 int tt_set_impl(int impl) {
-    if (impl != 0 && impl != 1) return fail(TT_E_ARG, "tt_set_impl: impl must be 0 (SIMT) or 1 (tcgen05)%s", "");
+    if (impl < 0 || impl > 2) return fail(TT_E_ARG, "tt_set_impl: impl must be 0 (SIMT), 1 (round-1 tcgen05) or 2 (warp-specialised tcgen05)%s", "");
     g_impl = impl;
     return TT_OK;
 }
@@ -764,7 +877,7 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
     if (!aligned16(planes) || !aligned16(wpack)) return fail(TT_E_ALIGN, "planes/wpack must be 16-byte aligned%s", "");
     const int64_t N = (int64_t)cfg->P * M;
     if (N == 0) return TT_OK;
-    if (g_impl == 1 && !(deformation && (normal || sdf_grad)) && N < 2147483647LL) {
+    if (g_impl >= 1 && !(deformation && (normal || sdf_grad)) && N < 2147483647LL) {
         bool done = false;
         TT_DISPATCH_C(cfg->C, {
             const size_t smg_n = (size_t)GeoSmem<kC, true>::TOTAL * 4, smg = (size_t)GeoSmem<kC, false>::TOTAL * 4;
@@ -777,19 +890,15 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
                     if (deformation) {      // field query of the mesh paths: SDF + deformation decoders on one gather
                         if (int e = set_smem(k_geo_tc<kC, false, true>, smg_d)) return e;
                         TT_LAUNCH((k_geo_tc<kC, false, true>), tc_grid(N), TC_THREADS, smg_d, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr, deformation);
+                        if (int e = check_launch("k_geo_tc")) return e;
                     } else if (want_n) {
-                        if (int e = set_smem(k_geo_tc<kC, true>, smg_n)) return e;
-                        TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg_n, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr, (float*)nullptr);
+                        if (int e = launch_geo_decoder<kC, true>(planes, wpack, cfg, src, N, sdf, sdf_orig, sdf_grad, normal, nullptr, (cudaStream_t)stream)) return e;
                     } else {
-                        if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
-                        TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr, (float*)nullptr);
+                        if (int e = launch_geo_decoder<kC, false>(planes, wpack, cfg, src, N, sdf, sdf_orig, sdf_grad, normal, nullptr, (cudaStream_t)stream)) return e;
                     }
-                    if (int e = check_launch("k_geo_tc")) return e;
                 }
                 if (features) {
-                    if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
-                    TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, (cudaStream_t)stream, planes, wpack, *cfg, src, N, features, (uint64_t*)nullptr);
-                    if (int e = check_launch("k_tex_tc")) return e;
+                    if (int e = launch_tex_decoder<kC>(planes, wpack, cfg, src, N, features, nullptr, (cudaStream_t)stream)) return e;
                 }
                 done = true;
             }
@@ -821,7 +930,7 @@ int tt_importance_sample(const float* planes, const float* wpack, const tt_confi
     if (!aligned16(planes) || !aligned16(wpack)) return fail(TT_E_ALIGN, "planes/wpack must be 16-byte aligned%s", "");
     if (n_rays <= 0) return TT_OK;
     const int64_t blocks = (n_rays + TPB - 1) / TPB;
-    if (g_impl == 1 && n_rays * n_imp < 2147483647LL) {
+    if (g_impl >= 1 && n_rays * n_imp < 2147483647LL) {
         bool done = false;
         TT_DISPATCH_C(cfg->C, {
             const size_t smg = (size_t)GeoSmem<kC, false>::TOTAL * 4;
@@ -838,9 +947,7 @@ int tt_importance_sample(const float* planes, const float* wpack, const tt_confi
                 TT_LAUNCH(k_classify, (unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream, *cfg, src, N, sdf, (float*)nullptr, (float*)nullptr, (float*)nullptr, list, lcount);
                 if (int e = check_launch("k_classify")) return e;
                 src.index = list; src.count = lcount;
-                if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
-                TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, (float*)nullptr, (float*)nullptr, (float*)nullptr, (uint64_t*)nullptr, (float*)nullptr);
-                if (int e = check_launch("k_geo_tc")) return e;
+                if (int e = launch_geo_decoder<kC, false>(planes, wpack, cfg, src, N, sdf, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream)) return e;
                 TT_LAUNCH(k_sampler_post, (unsigned)blocks, TPB, 0, (cudaStream_t)stream, *cfg, n_rays, n_imp, n_fine, (const float*)sdf, jitter0, jitter1, cdf, t_vals);
                 if (int e = check_launch("k_sampler_post")) return e;
                 done = true;
@@ -879,7 +986,7 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
     if (n_rays <= 0) return TT_OK;
     const RaySrc rs{rays_o, rays_d, t_starts, t_ends, t_stride, S};
     const int64_t blocks = (n_rays + TPB - 1) / TPB;
-    if (g_impl == 1 && scratch && n_rays * S < 2147483647LL) {
+    if (g_impl >= 1 && scratch && n_rays * S < 2147483647LL) {
         bool done = false;
         TT_DISPATCH_C(cfg->C, {
             const size_t smg = (size_t)GeoSmem<kC, true>::TOTAL * 4, smt = (size_t)TexSmem<kC>::TOTAL * 4;
@@ -901,17 +1008,13 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
                 TT_LAUNCH(k_classify, (unsigned)((N + 255) / 256), 256, 0, st, *cfg, src, N, p_sdf, sdf_orig, p_grad, (float*)nullptr, live, count + 1);
                 if (int e = check_launch("k_classify")) return e;
                 src.index = live; src.count = count + 1;
-                if (int e = set_smem(k_geo_tc<kC, true>, smg)) return e;
-                TT_LAUNCH((k_geo_tc<kC, true>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, src, N, p_sdf, sdf_orig, p_grad, (float*)nullptr, masks, (float*)nullptr);
-                if (int e = check_launch("k_geo_tc")) return e;
+                if (int e = launch_geo_decoder<kC, true>(planes, wpack, cfg, src, N, p_sdf, sdf_orig, p_grad, nullptr, masks, st)) return e;
                 src.index = nullptr; src.count = nullptr;
                 TT_LAUNCH(k_weights, (unsigned)((n_rays + RAY_WARPS - 1) / RAY_WARPS), RAY_WARPS * 32, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, acc, weights, p_trans, normal,
                           all_live ? (float*)nullptr : p_feat, all_live ? (int*)nullptr : live, count, all_live);
                 if (int e = check_launch("k_weights")) return e;
                 if (!all_live) { src.index = live; src.count = count; }
-                if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
-                TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, src, N, p_feat, masks);
-                if (int e = check_launch("k_tex_tc")) return e;
+                if (int e = launch_tex_decoder<kC>(planes, wpack, cfg, src, N, p_feat, masks, st)) return e;
                 TT_LAUNCH(k_accum_rgb, (unsigned)((n_rays + RAY_WARPS - 1) / RAY_WARPS), RAY_WARPS * 32, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, (const float*)p_trans, (const float*)p_feat, acc);
                 if (int e = check_launch("k_accum_rgb")) return e;
                 done = true;
@@ -939,7 +1042,7 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
                             const int* geo_count = nullptr, const int* tex_list = nullptr, const int* tex_count = nullptr) {
     const int64_t blocks = (N + TPB - 1) / TPB;
     if (blocks > 2147483647LL) return fail(TT_E_ARG, "too many sample points%s (%lld)", "", N);
-    if (g_impl == 1 && N < 2147483647LL) {
+    if (g_impl >= 1 && N < 2147483647LL) {
         bool done = false;
         TT_DISPATCH_C(cfg->C, {
             {
@@ -1029,7 +1132,7 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
     int* geo_list = nullptr; int* tex_list = nullptr; int* counts = nullptr;
     bool fwd_tc = false;     // did tt_render_fwd take the tensor-core path (and write the ReLU masks)?  Same test as there.
     TT_DISPATCH_C(cfg->C, { fwd_tc = (size_t)GeoSmem<kC, true>::TOTAL * 4 <= kMaxSmem && (size_t)TexSmem<kC>::TOTAL * 4 <= kMaxSmem; });
-    if (g_impl == 1 && fwd_tc && masks && N < 2147483647LL && (gplanes || gw)) {
+    if (g_impl >= 1 && fwd_tc && masks && N < 2147483647LL && (gplanes || gw)) {
         geo_list = reinterpret_cast<int*>(scratch + 7 * N); tex_list = geo_list + N; counts = tex_list + N;
         if (cudaMemsetAsync(counts, 0, 2 * sizeof(int), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
     }
@@ -1065,26 +1168,48 @@ int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cf
     if (int e = check_launch("k_geometry_bwd_seed")) return e;
     PtSrc src; src.points = points; src.M = M; src.rs = RaySrc{nullptr, nullptr, nullptr, nullptr, 0, 1}; src.rays_per_cache = 1;
     uint64_t* masks = nullptr;
-    if (g_impl == 1 && N < 2147483647LL) {      // forward ReLU masks of both decoders (tensor-core passes, 3xTF32)
+    if (g_impl >= 1 && N < 2147483647LL) {      // forward ReLU masks of both decoders (tensor-core passes, 3xTF32)
         bool done = false;
         TT_DISPATCH_C(cfg->C, {
             const size_t smt = (size_t)TexSmem<kC>::TOTAL * 4, smg = (size_t)GeoSmem<kC, false>::TOTAL * 4;
             if (smt <= kMaxSmem && smg <= kMaxSmem) {
                 masks = reinterpret_cast<uint64_t*>(scratch + ((10 * N + 3) / 4) * 4);
                 TcSrc ts{}; ts.mode = 0; ts.points = points; ts.M = M;
-                if (int e = set_smem(k_geo_tc<kC, false>, smg)) return e;
-                TT_LAUNCH((k_geo_tc<kC, false>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, ts, N, (float*)nullptr, (float*)nullptr,
-                          (float*)nullptr, (float*)nullptr, masks, (float*)nullptr);
-                if (int e = check_launch("k_geo_tc")) return e;
-                if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
-                TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, ts, N, (float*)nullptr, masks);
-                if (int e = check_launch("k_tex_tc")) return e;
+                if (int e = launch_geo_decoder<kC, false>(planes, wpack, cfg, ts, N, nullptr, nullptr, nullptr, nullptr, masks, st)) return e;
+                if (int e = launch_tex_decoder<kC>(planes, wpack, cfg, ts, N, nullptr, masks, st)) return e;
                 done = true;
             }
         });
         (void)done;
     }
     return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, masks, gplanes, gw, scratch + round4((size_t)N * 18 + 16), st);
+}
+
+size_t tt_wgrad_def_floats(int C) { return (size_t)64 * C + 4096 + 192; }
+
+int tt_field_bwd(const float* planes, const float* wpack, const tt_config* cfg, const float* points, int64_t M,
+                 const float* g_sdf, const float* g_deformation, float* scratch, float* gplanes, float* gw, float* gw_def,
+                 void* stream) {
+    if (int e = check_cfg(cfg)) return e;
+    if (!planes || !wpack || !points || !scratch) return fail(TT_E_ARG, "tt_field_bwd: NULL pointer%s", "");
+    if (!aligned16(planes) || !aligned16(wpack) || (gplanes && !aligned16(gplanes)))
+        return fail(TT_E_ALIGN, "planes/wpack/gplanes must be 16-byte aligned%s", "");
+    const int64_t N = (int64_t)cfg->P * M;
+    if (N <= 0) return TT_OK;
+    if (g_sdf && (gplanes || gw))
+        if (int e = tt_geometry_bwd(planes, wpack, cfg, points, M, g_sdf, nullptr, nullptr, nullptr, scratch, gplanes, gw, stream)) return e;
+    if (g_deformation && (gplanes || gw_def)) {
+        const int64_t blocks = (N + TPB - 1) / TPB;
+        if (blocks > 2147483647LL) return fail(TT_E_ARG, "tt_field_bwd: too many points%s (%lld)", "", N);
+        PtSrc src; src.points = points; src.M = M; src.rs = RaySrc{nullptr, nullptr, nullptr, nullptr, 0, 1}; src.rays_per_cache = 1;
+        TT_DISPATCH_C(cfg->C, {
+            const size_t sm = slab_bytes(kC + HID + HID + 4);
+            if (int e = set_smem(k_bwd_def<kC>, sm)) return e;
+            TT_LAUNCH(k_bwd_def<kC>, (unsigned)blocks, TPB, sm, (cudaStream_t)stream, planes, wpack, *cfg, src, N, g_deformation, gplanes, gw_def);
+        });
+        if (int e = check_launch("k_bwd_def")) return e;
+    }
+    return TT_OK;
 }
 
 int tt_composite_fwd(const float* alphas, const float* values, int64_t n_rays, int S, int D, float* weights,

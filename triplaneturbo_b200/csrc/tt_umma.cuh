@@ -75,6 +75,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// general mbarriers (producer / consumer hand-off between warp roles): `count` arrivals complete a phase
+__device__ __forceinline__ void mbar_init_n(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {        // release at CTA scope: prior shared-memory writes are visible
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int it = 0; it < (1 << 24) && !done; ++it)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done) __trap();                                       // never hang the GPU: abort the kernel instead
+}
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
@@ -104,6 +119,26 @@ __device__ __forceinline__ void umma_mma(const Umma& u, const BTile& b, int K, b
             umma_issue(d, u.tmem + TC_COL_AHI + a_col0 + ks * 8, dh, idesc, 1u);
         } else {
             umma_issue(d, u.tmem + TC_COL_AHI + a_col0 + ks * 8, dh, idesc, acc0);
+        }
+    }
+}
+// same with explicit TMEM columns of the A hi / lo parts and of the accumulator (inside the group's region)
+template <int PASSES>
+__device__ __forceinline__ void umma_mma_ex(const Umma& u, const BTile& b, int K, bool accumulate, uint32_t col_hi,
+                                            uint32_t col_lo, uint32_t col_d) {
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_tf32(b.N);
+    const uint32_t d = u.tmem + col_d;
+    for (int ks = 0; ks < K / 8; ++ks) {
+        const uint32_t acc0 = (accumulate || ks > 0) ? 1u : 0u;
+        const uint64_t dh = umma_desc(b.hi + ks * 2 * TC_LBO, TC_LBO, b.sbo);
+        if (PASSES == 3) {
+            const uint64_t dl = umma_desc(b.lo + ks * 2 * TC_LBO, TC_LBO, b.sbo);
+            umma_issue(d, u.tmem + col_lo + ks * 8, dh, idesc, acc0);
+            umma_issue(d, u.tmem + col_hi + ks * 8, dl, idesc, 1u);
+            umma_issue(d, u.tmem + col_hi + ks * 8, dh, idesc, 1u);
+        } else {
+            umma_issue(d, u.tmem + col_hi + ks * 8, dh, idesc, acc0);
         }
     }
 }
@@ -162,9 +197,18 @@ __device__ __forceinline__ void async_proxy_fence() {}
 __device__ __forceinline__ void tmem_alloc_warp(uint32_t* slot, uint32_t) { *slot = 0; }
 __device__ __forceinline__ void tmem_dealloc_warp(uint32_t, uint32_t) {}
 __device__ __forceinline__ void mbar_init(uint64_t* bar) { tt_emul::mbar_init(bar); }
+__device__ __forceinline__ void mbar_init_n(uint64_t* bar, uint32_t count) { tt_emul::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_init_fence() {}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { tt_emul::mbar_arrive(bar); }
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) { tt_emul::mbar_wait(bar, parity); }
 template <int PASSES>
 __device__ __forceinline__ void umma_mma(const Umma& u, const BTile& b, int K, bool accumulate, uint32_t a_col0 = 0) {
     tt_emul::umma(u.tmem, a_col0, b.hi, b.lo, b.sbo, b.N, K, accumulate, PASSES);
+}
+template <int PASSES>
+__device__ __forceinline__ void umma_mma_ex(const Umma& u, const BTile& b, int K, bool accumulate, uint32_t col_hi,
+                                            uint32_t col_lo, uint32_t col_d) {
+    tt_emul::umma_ex(u.tmem, col_hi, col_lo, col_d, b.hi, b.lo, b.sbo, b.N, K, accumulate, PASSES);
 }
 __device__ __forceinline__ void umma_mma_ss(const Umma& u, uint32_t a_saddr, uint32_t b_saddr, int N, uint32_t d_col,
                                             bool accumulate) {

@@ -23,8 +23,8 @@ from .compat import BaseModule, register
 
 class VanillaMLP(nn.Module):
     """Parameter container with the reference's layout (threestudio/models/networks.py:67-104): Linear(no bias),
-    ReLU, Linear, ReLU, Linear inside ``layers`` so checkpoints load unchanged.  Evaluation happens in the fused
-    kernels; this module is never called on the path."""
+    ReLU, Linear, ReLU, Linear inside ``layers`` so checkpoints load unchanged.  On the path the evaluation happens in
+    the fused kernels; ``forward`` exists for callers that evaluate a decoder on their own tensors."""
 
     def __init__(self, dim_in: int, dim_out: int, config: dict):
         super().__init__()
@@ -34,15 +34,18 @@ class VanillaMLP(nn.Module):
                                       "(configs/TriplaneTurbo_v1.yaml:86-91)")
         if config.get("activation", "ReLU") != "ReLU" or config.get("output_activation", "none") not in (None, "none"):
             raise NotImplementedError("only ReLU hidden activations and no output activation are supported")
-        self.layers = nn.Sequential(nn.Linear(dim_in, 64, bias=False), nn.ReLU(inplace=True),
-                                    nn.Linear(64, 64, bias=False), nn.ReLU(inplace=True),
+        self.layers = nn.Sequential(nn.Linear(dim_in, 64, bias=False), nn.ReLU(inplace=False),
+                                    nn.Linear(64, 64, bias=False), nn.ReLU(inplace=False),
                                     nn.Linear(64, dim_out, bias=False))
 
     def weights(self):
         return [self.layers[0].weight, self.layers[2].weight, self.layers[4].weight]
 
     def forward(self, x):
-        raise RuntimeError("VanillaMLP is evaluated inside the fused CUDA kernels; call the geometry instead")
+        """Direct evaluation for callers outside the fused path (networks.py:90-95, autocast off): plain library
+        linears.  The renderer / geometry never come here: they hand ``weights()`` to the CUDA kernels."""
+        with torch.autocast(device_type=x.device.type, enabled=False):
+            return self.layers(x.float())
 
 
 @register("few-step-triplane-dual-stable-diffusion")
@@ -131,10 +134,41 @@ class StableDiffusionTriplaneDualAttention(BaseModule):
         C_ = C2 // 2
         return torch.cat([triplane[:, 0:3, :C_], triplane[:, 3:6, C_:]], dim=1).contiguous()
 
+    def generate_space_cache(self, styles: Optional[Tensor] = None, text_embed: Optional[Tensor] = None):
+        """few_step…diffusion.py:156-165: ``space_generator(text_embed=, styles=)``.  The generator is outside this
+        package; with none attached this raises."""
+        if self.space_generator is None:
+            raise RuntimeError("no space_generator attached: pass space_cache= to the renderer "
+                               "(the SD generator is outside this package)")
+        return self.space_generator(text_embed=text_embed, styles=styles)
+
     # ------------------------------------------------------------------ the plugin surface
     def rescale_points(self, points: Tensor) -> Tensor:
         lo, hi = self.bbox[0], self.bbox[1]
         return (points - lo) / (hi - lo) * 2.0 - 1.0
+
+    def interpolate_encodings(self, points: Tensor, space_cache: Tensor, only_geo: bool = False):
+        """few_step…diffusion.py:198-258.  points [B,N,3] ALREADY rescaled to [-1,1]^3 (as the reference calls it);
+        returns the geometry encoding [B,N,C] (planes summed, ``v1``) and the texture encoding [B,N,3C] (planes
+        concatenated, ``v2``).  The reference rotates the cache into a zero tensor and makes two contiguous copies per
+        call; here the rotation is the one-time repack and the two samplers are ``tt_sample_planes_fwd`` launches.
+        Differentiable w.r.t. ``space_cache`` and ``points`` (to second order in ``points``, like the reference's
+        grid_sample_gradfix op)."""
+        from . import sampler
+        B = points.shape[0]
+        sc = self._check_cache(space_cache, B)
+        if sc.requires_grad and torch.is_grad_enabled():
+            planes = ops.RepackFunction.apply(sc, sc.shape[2], 0, 0)
+        else:
+            planes = ops.cached_planes(sc)
+        _, _, R, _, C_ = planes.shape
+        grid = sampler.project_onto_planes(sampler.PLANES, points.reshape(B, -1, 3)).float().contiguous()   # [3B,N,2]
+        geo = sampler.sample_planes(planes[:, 0:3].reshape(B * 3, R, R, C_), grid, 3, False)
+        geo = geo.view(*points.shape[:-1], -1)
+        if only_geo:
+            return geo
+        tex = sampler.sample_planes(planes[:, 3:6].reshape(B * 3, R, R, C_), grid, 3, True)
+        return geo, tex.view(*points.shape[:-1], -1)
 
     def forward(self, points: Tensor, space_cache: Tensor, output_normal: bool = False) -> Dict[str, Tensor]:
         """few_step…diffusion.py:273-351.  points [B,N,3] world coordinates."""
@@ -180,10 +214,14 @@ class StableDiffusionTriplaneDualAttention(BaseModule):
         B = points.shape[0]
         sc = self._check_cache(space_cache, B)
         pts = points.detach().reshape(B, -1, 3)
-        need_grad = torch.is_grad_enabled() and (sc.requires_grad or any(w.requires_grad for w in self.decoder_weights()))
+        dw = self._deformation_weights() if with_deformation else None
+        need_grad = torch.is_grad_enabled() and (sc.requires_grad or any(w.requires_grad for w in self.decoder_weights())
+                                                 or any(w.requires_grad for w in (dw or [])))
         if need_grad and not with_deformation:
             sdf = ops.GeometryFunction.apply(sc, *self.decoder_weights(), pts, self.path_scalars(), False)[0]
             return sdf, None
+        if need_grad:       # mesh renderer: gradients reach the planes, the SDF decoder and the deformation decoder
+            return ops.FieldFunction.apply(sc, *self.decoder_weights(), *dw, pts, self.path_scalars())
         planes = ops.cached_planes(sc)
         wpack = ops.cached_wpack(self.sdf_network.weights(), self.feature_network.weights(),
                                  self._deformation_weights(), self.plane_channels)

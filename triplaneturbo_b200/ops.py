@@ -334,7 +334,8 @@ class _PlaneCache:
 
 
 _planes_cache = _PlaneCache()
-_weights_cache = _PlaneCache()
+_weights_caches = {}      # one slot per weight-set shape (with / without the deformation decoder): no thrashing when
+                          # the renderer (6 tensors) and the field query (9 tensors) alternate inside a step
 
 
 def cached_planes(space_cache: Tensor) -> Tensor:
@@ -343,7 +344,32 @@ def cached_planes(space_cache: Tensor) -> Tensor:
 
 def cached_wpack(sdf_w, feat_w, def_w, C_) -> Tensor:
     ws = list(sdf_w) + list(feat_w or []) + list(def_w or [])
-    return _weights_cache.get(ws, lambda: pack_weights(sdf_w, feat_w, def_w, C_))
+    slot = _weights_caches.setdefault((len(ws), C_), _PlaneCache())
+    return slot.get(ws, lambda: pack_weights(sdf_w, feat_w, def_w, C_))
+
+
+def clear_caches():
+    """Drop the cached repacked planes / packed weights (they pin device memory until the next call replaces them)."""
+    _planes_cache.refs = _planes_cache.key = _planes_cache.val = None
+    _weights_caches.clear()
+
+
+class _impl_scope:
+    """Run a backward with the kernel family that produced its forward's saved state (the tensor-core forward saves
+    ReLU masks the SIMT forward never writes): ``set_impl`` between a forward and its backward must not mix them."""
+
+    def __init__(self, impl: int):
+        self.want, self.prev = int(impl), None
+
+    def __enter__(self):
+        cur = get_impl()
+        if cur != self.want:
+            self.prev = cur
+            set_impl(self.want)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            set_impl(self.prev)
 
 
 class RenderFunction(torch.autograd.Function):
@@ -363,7 +389,7 @@ class RenderFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[:8])
         out = render_fwd(planes, wpack, scalars, rays_o, rays_d, rays_per_cache, t_starts, t_ends, need_grad, extras)
         ctx.scalars, ctx.rays_per_cache, ctx.rgb_grad_scale = scalars, rays_per_cache, rgb_grad_scale
-        ctx.C = C_
+        ctx.C, ctx.impl = C_, get_impl()
         if need_grad:
             ctx.save_for_backward(planes, wpack, rays_o, rays_d, t_starts, t_ends, out["acc"], out["sdf"],
                                   out["sdf_grad"], out["features"], out["trans"], out["tex_masks"])
@@ -384,12 +410,13 @@ class RenderFunction(torch.autograd.Function):
             g_sdf = g_sdf_orig
         need_planes = ctx.needs_input_grad[0]
         need_w = any(ctx.needs_input_grad[1:7])
-        gplanes, gw, gis = render_bwd(planes, wpack, ctx.scalars, rays_o, rays_d, ctx.rays_per_cache, t0, t1,
-                                      {"acc": acc, "sdf": sdf, "sdf_grad": sdf_grad, "features": features,
-                                       "trans": trans, "tex_masks": tex_masks},
-                                      g_acc, None if g_sdf is None else g_sdf.reshape(-1), g_sdf_grad, g_normal,
-                                      g_features, None if g_weights is None else g_weights.reshape(-1),
-                                      ctx.rgb_grad_scale, need_planes, need_w, ctx.needs_input_grad[7])
+        with _impl_scope(ctx.impl):
+            gplanes, gw, gis = render_bwd(planes, wpack, ctx.scalars, rays_o, rays_d, ctx.rays_per_cache, t0, t1,
+                                          {"acc": acc, "sdf": sdf, "sdf_grad": sdf_grad, "features": features,
+                                           "trans": trans, "tex_masks": tex_masks},
+                                          g_acc, None if g_sdf is None else g_sdf.reshape(-1), g_sdf_grad, g_normal,
+                                          g_features, None if g_weights is None else g_weights.reshape(-1),
+                                          ctx.rgb_grad_scale, need_planes, need_w, ctx.needs_input_grad[7])
         g_sc = repack_planes_bwd(gplanes) if need_planes else None
         gws = split_wgrad(gw, ctx.C) if need_w else [None] * 6
         gws = [g if ctx.needs_input_grad[1 + i] else None for i, g in enumerate(gws)]
@@ -410,7 +437,7 @@ class GeometryFunction(torch.autograd.Function):
         wpack = cached_wpack([ws0, ws1, ws2], [wf0, wf1, wf2], None, C_)
         want = ["sdf", "sdf_orig", "features"] + (["normal", "sdf_grad"] if output_normal else [])
         out = geometry_fwd(planes, wpack, scalars, points, 0, want)
-        ctx.scalars, ctx.C, ctx.output_normal = scalars, C_, output_normal
+        ctx.scalars, ctx.C, ctx.output_normal, ctx.impl = scalars, C_, output_normal, get_impl()
         ctx.save_for_backward(planes, wpack, points)
         empty = torch.empty((0, 3), device=planes.device)
         return (out["sdf"].view(-1, 1), out["sdf_orig"].view(-1, 1), out["features"],
@@ -428,12 +455,94 @@ class GeometryFunction(torch.autograd.Function):
             g_normal = g_sdf_grad = None
         need_planes = ctx.needs_input_grad[0]
         need_w = any(ctx.needs_input_grad[1:7])
-        gplanes, gw = geometry_bwd(planes, wpack, ctx.scalars, points, g, g_features, g_normal, g_sdf_grad,
-                                   need_planes, need_w)
+        with _impl_scope(ctx.impl):
+            gplanes, gw = geometry_bwd(planes, wpack, ctx.scalars, points, g, g_features, g_normal, g_sdf_grad,
+                                       need_planes, need_w)
         g_sc = repack_planes_bwd(gplanes) if need_planes else None
         gws = split_wgrad(gw, ctx.C) if need_w else [None] * 6
         gws = [x if ctx.needs_input_grad[1 + i] else None for i, x in enumerate(gws)]
         return (g_sc, *gws, None, None, None)
+
+
+def field_bwd(planes: Tensor, wpack: Tensor, s: PathScalars, points: Tensor, g_sdf, g_deformation, need_planes=True,
+              need_w=True, need_wd=True):
+    """tt_field_bwd: backward of forward_field (sdf + deformation decoders) -> (gplanes, gw, gw_def)."""
+    P, _, R, _, C_ = planes.shape
+    dev = planes.device
+    points = _need(points, "points")
+    M = points.shape[1]
+    L = _lib()
+    cfg = _cfg(C_, R, P, 1, s)
+    scratch = torch.empty(L.tt_geometry_bwd_scratch_floats(C.byref(cfg), P * M), device=dev, dtype=torch.float32)
+    gplanes = torch.zeros_like(planes) if need_planes else None
+    gw = torch.zeros(L.tt_wgrad_floats(C_), device=dev, dtype=torch.float32) if need_w else None
+    gwd = torch.zeros(L.tt_wgrad_def_floats(C_), device=dev, dtype=torch.float32) if need_wd else None
+    gs = None if g_sdf is None else _need(g_sdf, "g_sdf")
+    gd = None if g_deformation is None else _need(g_deformation, "g_deformation")
+    with torch.cuda.device(dev):
+        _cabi.check(L, L.tt_field_bwd(_ptr(planes), _ptr(wpack), C.byref(cfg), _ptr(points), M, _ptr(gs), _ptr(gd),
+                                      _ptr(scratch), _ptr(gplanes), _ptr(gw), _ptr(gwd), _stream(dev)), "tt_field_bwd")
+    return gplanes, gw, gwd
+
+
+class FieldFunction(torch.autograd.Function):
+    """geometry.forward_field on a point list: sdf [N,1] and deformation [N,3] (tt_geometry_fwd / tt_field_bwd),
+    differentiable w.r.t. the space cache, the SDF decoder and the deformation decoder (the mesh renderer trains
+    through it, generative_space_mesh_rasterize_renderer.py:449-452)."""
+
+    @staticmethod
+    def forward(ctx, space_cache, ws0, ws1, ws2, wf0, wf1, wf2, wd0, wd1, wd2, points, scalars: PathScalars):
+        C_ = space_cache.shape[2]
+        planes = cached_planes(space_cache)
+        wpack = cached_wpack([ws0, ws1, ws2], [wf0, wf1, wf2], [wd0, wd1, wd2], C_)
+        out = geometry_fwd(planes, wpack, scalars, points, 0, ["sdf", "deformation"])
+        ctx.scalars, ctx.C, ctx.impl = scalars, C_, get_impl()
+        ctx.save_for_backward(planes, wpack, points)
+        return out["sdf"].view(-1, 1), out["deformation"]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_sdf, g_def):
+        planes, wpack, points = ctx.saved_tensors
+        need_planes = ctx.needs_input_grad[0]
+        need_w, need_wd = any(ctx.needs_input_grad[1:4]), any(ctx.needs_input_grad[7:10])
+        with _impl_scope(ctx.impl):
+            gplanes, gw, gwd = field_bwd(planes, wpack, ctx.scalars, points,
+                                         None if g_sdf is None else g_sdf.reshape(-1), g_def, need_planes, need_w,
+                                         need_wd)
+        g_sc = repack_planes_bwd(gplanes) if need_planes else None
+        gws = split_wgrad(gw, ctx.C)[:3] if need_w else [None] * 3
+        gws = [x if ctx.needs_input_grad[1 + i] else None for i, x in enumerate(gws)]
+        if need_wd:
+            C_ = ctx.C
+            gds = [gwd[:HIDDEN * C_].view(HIDDEN, C_), gwd[HIDDEN * C_:HIDDEN * C_ + HIDDEN * HIDDEN].view(HIDDEN, HIDDEN),
+                   gwd[HIDDEN * C_ + HIDDEN * HIDDEN:].view(3, HIDDEN)]
+            gds = [x if ctx.needs_input_grad[7 + i] else None for i, x in enumerate(gds)]
+        else:
+            gds = [None] * 3
+        return (g_sc, *gws, None, None, None, *gds, None, None)
+
+
+class RepackFunction(torch.autograd.Function):
+    """space cache [P,6,C,R,R] (NCHW) -> channel-last rotated planes [P,6,R,R,C]; a permutation, so the gradient is
+    tt_repack_planes_bwd.  ``off_geo/off_tex`` fold the channel split of ``decode`` (few_step…diffusion.py:180-196)."""
+
+    @staticmethod
+    def forward(ctx, space_cache, C_, off_geo, off_tex):
+        ctx.shape, ctx.off = tuple(space_cache.shape), (off_geo, off_tex)
+        return repack_planes(space_cache, C_, off_geo, off_tex)
+
+    @staticmethod
+    def backward(ctx, g):
+        P, _, Csrc, R, _ = ctx.shape
+        g_nchw = repack_planes_bwd(g.contiguous())                       # [P,6,C,R,R]
+        C_ = g_nchw.shape[2]
+        if Csrc == C_:
+            return g_nchw, None, None, None
+        full = torch.zeros(ctx.shape, device=g.device, dtype=torch.float32)
+        full[:, 0:3, ctx.off[0]:ctx.off[0] + C_] = g_nchw[:, 0:3]
+        full[:, 3:6, ctx.off[1]:ctx.off[1] + C_] = g_nchw[:, 3:6]
+        return full, None, None, None
 
 
 class CompositeFunction(torch.autograd.Function):

@@ -46,12 +46,14 @@ class LearnedVariance(nn.Module):
 
 
 class ImportanceEstimator(nn.Module):
-    """Drop-in for threestudio/models/estimators.py:15-118.
+    """Drop-in for threestudio/models/estimators.py:15-118, same ``sampling`` signature.
 
-    The reference evaluates caller-supplied proposal closures; on this path the only closure is the renderer's
-    SDF density (…sdf_volume_renderer.py:243-299), which ``tt_importance_sample`` fuses with both
-    nerfacc.importance_sampling calls, the transmittance scan and the final merge-sort.  The closure is therefore
-    described by data: ``prop_sigma_fns`` is a list holding one :class:`ProposalSpec`.
+    ``prop_sigma_fns`` is a list of callables ``(t_starts, t_ends) -> densities`` like the reference's.  The one closure
+    that exists on this path is the renderer's SDF density (…sdf_volume_renderer.py:243-299); the renderer passes it as
+    a :class:`ProposalSpec` (a callable that also carries the data the closure captured), and ``sampling`` then runs the
+    whole estimator -- both nerfacc.importance_sampling calls, the density evaluation, the transmittance scan and the
+    final merge-sort -- as ONE fused call (``tt_importance_sample``).  Any other callable takes the general route:
+    the estimator's steps as written in the reference, on torch device tensors, with the closure called as is.
     """
 
     @dataclass
@@ -63,30 +65,97 @@ class ImportanceEstimator(nn.Module):
         rays_d: Tensor
         rays_per_cache: int
 
+        def __call__(self, t_starts: Tensor, t_ends: Tensor) -> Tensor:
+            """The proposal closure itself (…sdf_volume_renderer.py:243-299): NeuS density of the SDF at the interval
+            midpoints.  Used when a caller evaluates the closure directly; ``sampling`` fuses it instead."""
+            n, m = t_starts.shape
+            t_mid = (t_starts + t_ends) / 2.0
+            pos = self.rays_o.view(-1, 1, 3) + self.rays_d.view(-1, 1, 3) * t_mid[..., None]
+            P = self.planes.shape[0]
+            sdf = ops.geometry_fwd(self.planes, self.wpack, self.scalars, pos.reshape(P, -1, 3).contiguous(), 0,
+                                   ["sdf"])["sdf"].view(n, m)
+            s = self.scalars
+            prev_cdf = torch.sigmoid((sdf + s.render_step_size * 0.5) * s.inv_std)
+            next_cdf = torch.sigmoid((sdf - s.render_step_size * 0.5) * s.inv_std)
+            alpha = ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0.0, 1.0)
+            return alpha / s.render_step_size
+
+    @staticmethod
+    def _quantiles(n: int, n_rays: int, jitter: Optional[Tensor], device) -> Tensor:
+        j = torch.arange(n + 1, dtype=torch.float32, device=device)
+        if jitter is None:
+            return (j / float(n))[None, :].expand(n_rays, -1).contiguous()
+        return ((j[None, :] + jitter[:, None]) / float(n + 1)).contiguous()
+
+    @staticmethod
+    def _importance_sampling(vals: Tensor, cdfs: Tensor, n: int, jitter: Optional[Tensor]) -> Tensor:
+        """nerfacc.pdf.importance_sampling on dense rays: n+1 edge quantiles inverted through the piece-wise linear
+        CDF (same conventions as the fused kernel: u_j = j/n, or (j+b)/(n+1) with one jitter b per ray)."""
+        n_rays, n_in = cdfs.shape
+        u = ImportanceEstimator._quantiles(n, n_rays, jitter, cdfs.device)
+        p = torch.searchsorted(cdfs.contiguous(), u, right=True).clamp(1, n_in - 1)
+        c0, c1 = torch.gather(cdfs, 1, p - 1), torch.gather(cdfs, 1, p)
+        v0, v1 = torch.gather(vals, 1, p - 1), torch.gather(vals, 1, p)
+        den = c1 - c0
+        frac = torch.where(den > 0, (u - c0) / den, torch.zeros_like(u)).clamp(0.0, 1.0)
+        return v0 + frac * (v1 - v0)
+
     @torch.no_grad()
     def sampling(self, prop_sigma_fns: List[Any], prop_samples: List[int], num_samples: int, n_rays: int,
                  near_plane: float, far_plane: float, sampling_type: str = "uniform", stratified: bool = False,
-                 requires_grad: bool = False, jitters: Optional[Tuple[Tensor, Tensor]] = None
+                 requires_grad: bool = False, jitters: Optional[Tuple[Tensor, ...]] = None
                  ) -> Tuple[Tensor, Tensor]:
         assert len(prop_sigma_fns) == len(prop_samples), \
             "The number of proposal networks and the number of samples should be the same."
-        if len(prop_sigma_fns) != 1 or not isinstance(prop_sigma_fns[0], ImportanceEstimator.ProposalSpec):
-            raise NotImplementedError("one proposal level described by a ProposalSpec is supported")
-        if sampling_type != "uniform":
-            raise NotImplementedError("sampling_type must be 'uniform' (configs/TriplaneTurbo_v1.yaml)")
-        spec = prop_sigma_fns[0]
-        s = ops.PathScalars(**{**spec.scalars.__dict__, "near_plane": float(near_plane), "far_plane": float(far_plane)})
-        j0 = j1 = None
-        if stratified:
-            if jitters is None:   # one offset per ray and per importance_sampling call (nerfacc draws its own)
-                j0 = torch.rand(n_rays, device=spec.rays_o.device)
-                j1 = torch.rand(n_rays, device=spec.rays_o.device)
-            else:
-                j0, j1 = jitters
-        t_vals = ops.importance_sample(spec.planes, spec.wpack, s, spec.rays_o, spec.rays_d, spec.rays_per_cache,
-                                       int(prop_samples[0]), int(num_samples), j0, j1)
-        assert t_vals.shape[0] == n_rays
-        return t_vals[:, :-1], t_vals[:, 1:]
+        if sampling_type not in ("uniform", "lindisp"):
+            raise ValueError(f"Unknown transform_type: {sampling_type}")
+        fused = (len(prop_sigma_fns) == 1 and isinstance(prop_sigma_fns[0], ImportanceEstimator.ProposalSpec)
+                 and sampling_type == "uniform")
+        if fused:
+            spec = prop_sigma_fns[0]
+            s = ops.PathScalars(**{**spec.scalars.__dict__, "near_plane": float(near_plane),
+                                   "far_plane": float(far_plane)})
+            j0 = j1 = None
+            if stratified:
+                if jitters is None:   # one offset per ray and per importance_sampling call (nerfacc draws its own)
+                    j0 = torch.rand(n_rays, device=spec.rays_o.device)
+                    j1 = torch.rand(n_rays, device=spec.rays_o.device)
+                else:
+                    j0, j1 = jitters
+            t_vals = ops.importance_sample(spec.planes, spec.wpack, s, spec.rays_o, spec.rays_d, spec.rays_per_cache,
+                                           int(prop_samples[0]), int(num_samples), j0, j1)
+            assert t_vals.shape[0] == n_rays
+            return t_vals[:, :-1], t_vals[:, 1:]
+        # ---- general route: arbitrary closures, the estimator's steps as in estimators.py:63-101 ----------------
+        dev = next((getattr(f, "rays_o", None) for f in prop_sigma_fns if hasattr(f, "rays_o")), None)
+        dev = dev.device if dev is not None else torch.device("cuda", torch.cuda.current_device())
+
+        def stot(sv):
+            if sampling_type == "uniform":
+                return sv * far_plane + (1 - sv) * near_plane
+            return 1.0 / (sv * (1.0 / far_plane) + (1 - sv) * (1.0 / near_plane))
+        n_lv = len(prop_sigma_fns)
+        if stratified and jitters is None:
+            jitters = tuple(torch.rand(n_rays, device=dev) for _ in range(n_lv + 1))
+        vals = torch.cat([torch.zeros((n_rays, 1), device=dev), torch.ones((n_rays, 1), device=dev)], dim=-1)
+        cdfs = vals.clone()
+        t_vals = None
+        for lv, (level_fn, level_samples) in enumerate(zip(prop_sigma_fns, prop_samples)):
+            vals = self._importance_sampling(vals, cdfs, int(level_samples), jitters[lv] if stratified else None)
+            t_vals = stot(vals)
+            t0, t1 = t_vals[..., :-1], t_vals[..., 1:]
+            with torch.set_grad_enabled(requires_grad):
+                sigmas = level_fn(t0, t1)
+                assert sigmas.shape == t0.shape
+                sdt = sigmas * (t1 - t0)
+                excl = torch.cumsum(torch.cat([torch.zeros_like(sdt[:, :1]), sdt[:, :-1]], dim=-1), dim=-1)
+                trans = torch.exp(-excl)
+                cdfs = 1.0 - torch.cat([trans, torch.zeros_like(trans[:, :1])], dim=-1)
+        vals_f = self._importance_sampling(vals, cdfs, int(num_samples), jitters[n_lv] if stratified else None)
+        t_fine = stot(vals_f)
+        t_all = t_fine if t_vals is None else torch.cat([t_vals, t_fine], dim=-1)
+        t_all, _ = torch.sort(t_all, dim=-1)
+        return t_all[..., :-1], t_all[..., 1:]
 
 
 @register("generative-space-sdf-volume-renderer")
@@ -111,6 +180,9 @@ class GenerativeSpaceSDFVolumeRenderer(BaseModule):
         rgb_grad_shrink: Any = 1.0
         normal_direction: str = "camera"
         return_samples: bool = True        # training extras (weights, sdf, normal, … per sample), REN:532-545
+        anneal_cos_in_update_step: bool = False   # the reference's GenerativeSpaceSDFVolumeRenderer.update_step
+                                                  # (…sdf_volume_renderer.py:548-553) never touches cos_anneal_ratio,
+                                                  # so it stays 1.0; True applies neus_volume_renderer.py:87-91
 
     cfg: Config
 
@@ -220,6 +292,8 @@ class GenerativeSpaceSDFVolumeRenderer(BaseModule):
                 bg_color = bgm(dirs=rays_d, text_embed=kwargs.get("text_embed_bg", text_embed))
             else:
                 bg_color = bgm(dirs=rays_d)
+        if not self.training and Pc != B:
+            num_views_per_batch = 1      # REN:150-176: eval renders view by view, each view is its own "front"
         out = compose_images(acc, bg_color, camera_distances, c2w, B, H, W, self.cfg.normal_direction,
                              num_views_per_batch)
         if out["comp_rgb_bg"].dim() < 4:
@@ -243,16 +317,20 @@ class GenerativeSpaceSDFVolumeRenderer(BaseModule):
 
     def update_step(self, epoch: int, global_step: int, on_load_weights: bool = False) -> None:
         self.rgb_grad_shrink = C(self.cfg.rgb_grad_shrink, epoch, global_step)
-        # threestudio/models/renderers/neus_volume_renderer.py:87-91
-        self.cos_anneal_ratio = 1.0 if self.cfg.cos_anneal_end_steps == 0 else \
-            min(1.0, global_step / self.cfg.cos_anneal_end_steps)
+        if self.cfg.anneal_cos_in_update_step:      # threestudio/models/renderers/neus_volume_renderer.py:87-91
+            self.cos_anneal_ratio = 1.0 if self.cfg.cos_anneal_end_steps == 0 else \
+                min(1.0, global_step / self.cfg.cos_anneal_end_steps)
 
-    def train(self, mode=True):
+    def train(self, mode=True):                     # …sdf_volume_renderer.py:555-565
         self.randomized = mode and self.cfg.randomized
+        if self.geometry is not None and hasattr(self.geometry, "train"):
+            self.geometry.train(mode)
         return super().train(mode=mode)
 
     def eval(self):
         self.randomized = False
+        if self.geometry is not None and hasattr(self.geometry, "eval"):
+            self.geometry.eval()
         return super().eval()
 
 

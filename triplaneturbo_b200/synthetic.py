@@ -59,3 +59,33 @@ def random_decoder(C: int, seed: int = 1, gain: float = 1.5) -> Dict[str, torch.
     for name, din, dout in (("sdf", C, 1), ("feature", 3 * C, 3), ("deformation", C, 3)):
         out[f"w_{name}_0"], out[f"w_{name}_1"], out[f"w_{name}_2"] = lin(64, din), lin(64, 64), lin(dout, 64)
     return out
+
+
+def build_plugins(fx, device, n_samples=64, n_imp=128, normal_direction="camera", rgb_grad_shrink=1.0, **renderer_over):
+    """Geometry + renderer plugins, created by registry name like the reference's systems do
+    (threestudio/systems/base.py:292-303), holding the weights of ``fx`` (keys ``w_{sdf,feature,deformation}_{0,1,2}``,
+    ``space_cache`` only for its channel count).  Shipped configuration: configs/TriplaneTurbo_v1.yaml:73-150."""
+    import triplaneturbo_b200 as tt
+    C_ = fx["space_cache"].shape[2]
+    geom = tt.find("few-step-triplane-dual-stable-diffusion")(dict(
+        radius=1.0, normal_type="analytic", sdf_bias="sphere", sdf_bias_params=0.5, rotate_planes="v1",
+        split_channels="v1", geo_interpolate="v1", tex_interpolate="v2",
+        space_generator_config={"output_dim": 2 * C_}, isosurface_deformable_grid=True)).to(device)
+    sd = {}
+    for name in ("sdf", "feature", "deformation"):
+        for i, idx in enumerate((0, 2, 4)):
+            if f"w_{name}_{i}" in fx:
+                sd[f"{name}_network.layers.{idx}.weight"] = fx[f"w_{name}_{i}"]
+    missing = geom.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    material = tt.find("no-material")(dict(n_output_dims=3, color_activation="sigmoid-mipnerf", requires_normal=True))
+    background = tt.find("solid-color-background")({}).to(device)
+    cfg = dict(radius=1.0, use_volsdf=False, trainable_variance=False, learned_variance_init=0.4605,
+               rgb_grad_shrink=rgb_grad_shrink, estimator="importance", num_samples_per_ray=n_samples,
+               num_samples_per_ray_importance=n_imp, near_plane=0.1, far_plane=4.0, train_chunk_size=0, randomized=False,
+               normal_direction=normal_direction, eval_chunk_size=500)
+    cfg.update(renderer_over)
+    rend = tt.find("generative-space-sdf-volume-renderer")(cfg, geometry=geom, material=material,
+                                                           background=background).to(device)
+    rend.update_step(0, 0)
+    return geom, rend
