@@ -229,6 +229,46 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// image-space variant: rays of a pinhole camera through a W x W image; order = (16x8 pixel patch, sample, pixel in patch), so a
+// 128-point tile holds ONE sample index of 128 ADJACENT rays (their 2x2 footprints overlap) instead of 128 samples of one ray
+static std::vector<Pt> make_points_patch(int W, int S, int P, bool patch_major, unsigned seed) {
+    std::mt19937 rng(seed);
+    std::uniform_real_distribution<float> U(0.f, 1.f);
+    std::vector<Pt> pts;
+    const float o[3] = {2.0f, 0.6f, 0.9f};
+    float f[3] = {-o[0], -o[1], -o[2]}, fl = std::sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+    for (auto& v : f) v /= fl;
+    float r[3] = {f[1], -f[0], 0.f}, rl = std::sqrt(r[0] * r[0] + r[1] * r[1]);
+    for (auto& v : r) v /= rl;
+    const float u[3] = {r[1] * f[2] - r[2] * f[1], r[2] * f[0] - r[0] * f[2], r[0] * f[1] - r[1] * f[0]};
+    const float tanh_ = 0.5774f;
+    auto ray_pts = [&](int px, int py, std::vector<Pt>& out) {
+        const float sx = ((px + 0.5f) / W * 2 - 1) * tanh_, sy = ((py + 0.5f) / W * 2 - 1) * tanh_;
+        float d[3]; float dl = 0;
+        for (int a = 0; a < 3; ++a) { d[a] = f[a] + sx * r[a] + sy * u[a]; dl += d[a] * d[a]; }
+        dl = std::sqrt(dl);
+        for (auto& v : d) v /= dl;
+        for (int i = 0; i < S; ++i) {
+            const float t = 1.2f + 2.0f * (i + 0.5f) / S;
+            out.push_back(Pt{o[0] + d[0] * t, o[1] + d[1] * t, o[2] + d[2] * t, 0});
+        }
+    };
+    if (!patch_major) {
+        for (int py = 0; py < W; ++py) for (int px = 0; px < W; ++px) ray_pts(px, py, pts);
+    } else {
+        for (int by = 0; by < W; by += 8) for (int bx = 0; bx < W; bx += 16) {
+            std::vector<Pt> tmp;
+            for (int y = 0; y < 8; ++y) for (int x = 0; x < 16; ++x) ray_pts(bx + x, by + y, tmp);
+            for (int i = 0; i < S; ++i) for (int q = 0; q < 128; ++q) pts.push_back(tmp[(size_t)q * S + i]);
+        }
+    }
+    // keep in-box points only (the kernels skip the others)
+    std::vector<Pt> in;
+    for (auto& p : pts) if (std::fabs(p.x) < 1.004f && std::fabs(p.y) < 1.004f && std::fabs(p.z) < 1.004f) in.push_back(p);
+    (void)P; (void)U; (void)rng;
+    return in;
+}
+
 static std::vector<Pt> make_points(int n_rays, int S, int P, float spread, unsigned seed) {
     std::mt19937 rng(seed);
     std::uniform_real_distribution<float> U(0.f, 1.f);
@@ -279,7 +319,7 @@ static float time_ms(F f, int warm = 2, int iters = 5) {
 }
 
 template <int C>
-static void run(int P, int R, int n_rays, int S, float spread) {
+static void run(int P, int R, int n_rays, int S, float spread, int patch = -1) {
     const size_t ps = (size_t)R * R * C, nplane = (size_t)P * 6 * ps;
     std::vector<float> h(nplane);
     std::mt19937 rng(1);
@@ -287,7 +327,8 @@ static void run(int P, int R, int n_rays, int S, float spread) {
     for (auto& v : h) v = U(rng);
     float* planes; CK(cudaMalloc(&planes, nplane * 4));
     CK(cudaMemcpy(planes, h.data(), nplane * 4, cudaMemcpyHostToDevice));
-    std::vector<Pt> pts = make_points(n_rays, S, P, spread, 7);
+    std::vector<Pt> pts = patch < 0 ? make_points(n_rays, S, P, spread, 7) : make_points_patch(512, 128, P, patch == 1, 7);
+    if (patch >= 0) printf("-- 512^2 pinhole rays x 128 samples, order: %s\n", patch ? "(16x8 pixel patch, sample, pixel)" : "ray-major");
     const int n = (int)pts.size();
     Pt* dp; CK(cudaMalloc(&dp, (size_t)n * sizeof(Pt)));
     CK(cudaMemcpy(dp, pts.data(), (size_t)n * sizeof(Pt), cudaMemcpyHostToDevice));
@@ -310,9 +351,9 @@ static void run(int P, int R, int n_rays, int S, float spread) {
                std::fabs(per - ref) / (std::fabs(ref) + 1e-30));
     };
     // ---- LDG path
-    auto ldg = [&](auto gtag, const char* name) {
+    auto ldg = [&](auto gtag, const char* name, size_t extra = 0) {
         constexpr int G = decltype(gtag)::value;
-        const size_t sm = (size_t)G * (128 * 24 + 128 + 128 * (C + 4)) * 4;
+        const size_t sm = (size_t)G * (128 * 24 + 128 + 128 * (C + 4)) * 4 + extra;
         CK(cudaFuncSetAttribute(k_ldg<C, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         CK(cudaMemset(out, 0, 8));
         const float ms = time_ms([&]() { k_ldg<C, G><<<sms, G * 128, sm>>>(planes, dp, n, R, out); });
@@ -322,7 +363,13 @@ static void run(int P, int R, int n_rays, int S, float spread) {
     ldg(std::integral_constant<int, 1>{}, "ldg  4 warps/SM (24 loads in flight)");
     ldg(std::integral_constant<int, 2>{}, "ldg  8 warps/SM");
     ldg(std::integral_constant<int, 3>{}, "ldg 12 warps/SM");
+    // the decoder kernels keep 160-215 KB of shared memory: what the same gather gets with the L1 that is left
+    ldg(std::integral_constant<int, 1>{}, "ldg  4 warps/SM, +130 KB smem (L1 ~ 64 KB)", 130 * 1024);
+    ldg(std::integral_constant<int, 1>{}, "ldg  4 warps/SM, +170 KB smem (L1 ~ 28 KB)", 170 * 1024);
+    ldg(std::integral_constant<int, 2>{}, "ldg  8 warps/SM, +100 KB smem (L1 ~ 64 KB)", 100 * 1024);
+    ldg(std::integral_constant<int, 2>{}, "ldg  8 warps/SM, +130 KB smem (L1 ~ 28 KB)", 130 * 1024);
 
+    if (patch >= 0) { CK(cudaFree(planes)); CK(cudaFree(dp)); CK(cudaFree(out)); return; }
     // ---- TMA path
     EncodeFn encode = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -369,5 +416,7 @@ int main(int argc, char** argv) {
     run<32>(4, 256, n_rays, 128, 0.05f);
     run<32>(4, 256, n_rays, 128, 0.4f);
     run<40>(4, 256, n_rays, 128, 0.05f);
+    run<32>(4, 256, n_rays, 128, 0.05f, 0);
+    run<32>(4, 256, n_rays, 128, 0.05f, 1);
     return 0;
 }

@@ -97,16 +97,18 @@ static unsigned tc_grid(int64_t n_points) {
     const int64_t ctas = (n_points + TC_THREADS - 1) / TC_THREADS;
     return (unsigned)(ctas < (int64_t)num_sms() ? (ctas < 1 ? 1 : ctas) : num_sms());
 }
-// SDF decoder on a point list: warp-specialised kernel (impl 2) or the round-1 kernel (impl 1)
+// SDF decoder on a point list: warp-specialised kernel (impl 2) or the round-1 kernel (impl 1).  vscratch: the L2-resident
+// tangent-row buffer of the warp-specialised normal path (ws_vscratch_floats(num_sms(), C) floats), may be NULL.
 template <int kC, bool NORMAL>
 static int launch_geo_decoder(const float* planes, const float* wpack, const tt_config* cfg, const TcSrc& src, int64_t N,
-                              float* sdf, float* sdf_orig, float* grad, float* normal, uint64_t* masks, cudaStream_t st) {
+                              float* sdf, float* sdf_orig, float* grad, float* normal, uint64_t* masks, float* vscratch,
+                              cudaStream_t st) {
     const size_t smw = (size_t)GeoWs<kC, NORMAL>::TOTAL * 4;
-    if (g_impl == 2 && smw <= kMaxSmem) {
+    if (g_impl == 2 && smw <= kMaxSmem && (!NORMAL || vscratch)) {
         if (int e = set_smem(k_geo_ws<kC, NORMAL>, smw)) return e;
-        const int64_t tiles = (N + TC_GROUP - 1) / TC_GROUP;
-        const unsigned grid = (unsigned)(tiles < (int64_t)num_sms() ? (tiles < 1 ? 1 : tiles) : num_sms());
-        TT_LAUNCH((k_geo_ws<kC, NORMAL>), grid, WS_THREADS, smw, st, planes, wpack, *cfg, src, N, sdf, sdf_orig, grad, normal, masks);
+        const int64_t ctas = (N + WS_CG * TC_GROUP - 1) / (WS_CG * TC_GROUP);
+        const unsigned grid = (unsigned)(ctas < (int64_t)num_sms() ? (ctas < 1 ? 1 : ctas) : num_sms());
+        TT_LAUNCH((k_geo_ws<kC, NORMAL>), grid, WS_THREADS, smw, st, planes, wpack, *cfg, src, N, sdf, sdf_orig, grad, normal, masks, vscratch);
         return check_launch("k_geo_ws");
     }
     const size_t smg = (size_t)GeoSmem<kC, NORMAL>::TOTAL * 4;
@@ -114,13 +116,21 @@ static int launch_geo_decoder(const float* planes, const float* wpack, const tt_
     TT_LAUNCH((k_geo_tc<kC, NORMAL>), tc_grid(N), TC_THREADS, smg, st, planes, wpack, *cfg, src, N, sdf, sdf_orig, grad, normal, masks, (float*)nullptr);
     return check_launch("k_geo_tc");
 }
+static size_t round4(size_t n) { return (n + 3) / 4 * 4; }
+static size_t ws_scratch_floats() { return ws_vscratch_floats(num_sms(), 40) + 16; }      // largest C of the ws kernels
 
 // colour decoder on a point list
 template <int kC>
 static int launch_tex_decoder(const float* planes, const float* wpack, const tt_config* cfg, const TcSrc& src, int64_t N,
                               float* features, uint64_t* masks, cudaStream_t st) {
+    // The warp-specialised colour kernel is parity-green but slower than the two-group kernel at both bench configurations
+    // (config 3: 185.6 vs 164.7 ms, config 2: 47.6 vs 43.6 ms, profiles/r02_bench_ws3_*.json): one gather warpgroup issues
+    // fewer loads than two groups gathering for themselves.  Opt in with -DTT_TEX_WS=1.
+#ifndef TT_TEX_WS
+#define TT_TEX_WS 0
+#endif
     const size_t smw = (size_t)TexWs<kC>::TOTAL * 4;
-    if (g_impl == 2 && smw <= kMaxSmem) {
+    if (TT_TEX_WS && g_impl == 2 && smw <= kMaxSmem) {
         if (int e = set_smem(k_tex_ws<kC>, smw)) return e;
         const int64_t tiles = (N + TC_GROUP - 1) / TC_GROUP;
         const unsigned grid = (unsigned)(tiles < (int64_t)num_sms() ? (tiles < 1 ? 1 : tiles) : num_sms());
@@ -786,6 +796,16 @@ __global__ void k_composite_bwd(const float* __restrict__ alphas, const float* _
 extern "C" {
 
 int tt_version(void) { return TT_VERSION; }
+#if defined(TT_WS_TIMING) && !defined(TT_EMUL)
+// debug builds only: phase anatomy of k_geo_ws (cycles accumulated by CTA 0), reset after reading
+extern "C" int tt_debug_ws_prof(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, tt::g_ws_prof, sizeof(unsigned long long) * 32);
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(tt::g_ws_prof, z, sizeof(z));
+    return 0;
+}
+#endif
 const char* tt_last_error(void) { return g_err; }
 int64_t tt_launch_count(void) { return g_launches.load(); }
 int tt_profile_begin(void) {
@@ -892,9 +912,9 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
                         TT_LAUNCH((k_geo_tc<kC, false, true>), tc_grid(N), TC_THREADS, smg_d, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr, deformation);
                         if (int e = check_launch("k_geo_tc")) return e;
                     } else if (want_n) {
-                        if (int e = launch_geo_decoder<kC, true>(planes, wpack, cfg, src, N, sdf, sdf_orig, sdf_grad, normal, nullptr, (cudaStream_t)stream)) return e;
+                        if (int e = launch_geo_decoder<kC, true>(planes, wpack, cfg, src, N, sdf, sdf_orig, sdf_grad, normal, nullptr, nullptr, (cudaStream_t)stream)) return e;
                     } else {
-                        if (int e = launch_geo_decoder<kC, false>(planes, wpack, cfg, src, N, sdf, sdf_orig, sdf_grad, normal, nullptr, (cudaStream_t)stream)) return e;
+                        if (int e = launch_geo_decoder<kC, false>(planes, wpack, cfg, src, N, sdf, sdf_orig, sdf_grad, normal, nullptr, nullptr, (cudaStream_t)stream)) return e;
                     }
                 }
                 if (features) {
@@ -947,7 +967,7 @@ int tt_importance_sample(const float* planes, const float* wpack, const tt_confi
                 TT_LAUNCH(k_classify, (unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream, *cfg, src, N, sdf, (float*)nullptr, (float*)nullptr, (float*)nullptr, list, lcount);
                 if (int e = check_launch("k_classify")) return e;
                 src.index = list; src.count = lcount;
-                if (int e = launch_geo_decoder<kC, false>(planes, wpack, cfg, src, N, sdf, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream)) return e;
+                if (int e = launch_geo_decoder<kC, false>(planes, wpack, cfg, src, N, sdf, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream)) return e;
                 TT_LAUNCH(k_sampler_post, (unsigned)blocks, TPB, 0, (cudaStream_t)stream, *cfg, n_rays, n_imp, n_fine, (const float*)sdf, jitter0, jitter1, cdf, t_vals);
                 if (int e = check_launch("k_sampler_post")) return e;
                 done = true;
@@ -973,7 +993,7 @@ static int check_rays(const char* who, const tt_config* cfg, const float* rays_o
     return TT_OK;
 }
 
-size_t tt_render_fwd_scratch_floats(int64_t n_rays, int S) { return (size_t)n_rays * (size_t)S * 9 + 16; }
+size_t tt_render_fwd_scratch_floats(int64_t n_rays, int S) { return round4((size_t)n_rays * (size_t)S * 9 + 16) + ws_scratch_floats(); }
 
 int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg, const float* rays_o,
                   const float* rays_d, int64_t n_rays, const float* t_starts, const float* t_ends, int64_t t_stride,
@@ -1008,7 +1028,7 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
                 TT_LAUNCH(k_classify, (unsigned)((N + 255) / 256), 256, 0, st, *cfg, src, N, p_sdf, sdf_orig, p_grad, (float*)nullptr, live, count + 1);
                 if (int e = check_launch("k_classify")) return e;
                 src.index = live; src.count = count + 1;
-                if (int e = launch_geo_decoder<kC, true>(planes, wpack, cfg, src, N, p_sdf, sdf_orig, p_grad, nullptr, masks, st)) return e;
+                if (int e = launch_geo_decoder<kC, true>(planes, wpack, cfg, src, N, p_sdf, sdf_orig, p_grad, nullptr, masks, scratch + round4((size_t)N * 9 + 16), st)) return e;
                 src.index = nullptr; src.count = nullptr;
                 TT_LAUNCH(k_weights, (unsigned)((n_rays + RAY_WARPS - 1) / RAY_WARPS), RAY_WARPS * 32, 0, st, *cfg, rt, n_rays, (const float*)p_sdf, (const float*)p_grad, acc, weights, p_trans, normal,
                           all_live ? (float*)nullptr : p_feat, all_live ? (int*)nullptr : live, count, all_live);
@@ -1034,7 +1054,6 @@ int tt_render_fwd(const float* planes, const float* wpack, const tt_config* cfg,
 static size_t hid_floats(const tt_config* cfg) {      // hidden-gradient planes of the colour backward, [P][3][R*R][64]
     return cfg ? (size_t)cfg->P * 3 * (size_t)cfg->R * (size_t)cfg->R * 64 : 0;
 }
-static size_t round4(size_t n) { return (n + 3) / 4 * 4; }
 
 static int launch_point_bwd(const float* planes, const float* wpack, const tt_config* cfg, const PtSrc& src, int64_t N,
                             const float* gs, const float* u, const float* gf, const uint64_t* tex_masks, float* gplanes,
@@ -1175,7 +1194,7 @@ int tt_geometry_bwd(const float* planes, const float* wpack, const tt_config* cf
             if (smt <= kMaxSmem && smg <= kMaxSmem) {
                 masks = reinterpret_cast<uint64_t*>(scratch + ((10 * N + 3) / 4) * 4);
                 TcSrc ts{}; ts.mode = 0; ts.points = points; ts.M = M;
-                if (int e = launch_geo_decoder<kC, false>(planes, wpack, cfg, ts, N, nullptr, nullptr, nullptr, nullptr, masks, st)) return e;
+                if (int e = launch_geo_decoder<kC, false>(planes, wpack, cfg, ts, N, nullptr, nullptr, nullptr, nullptr, masks, nullptr, st)) return e;
                 if (int e = launch_tex_decoder<kC>(planes, wpack, cfg, ts, N, nullptr, masks, st)) return e;
                 done = true;
             }

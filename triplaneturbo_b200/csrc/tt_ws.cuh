@@ -1,131 +1,69 @@
 // Warp-specialised tensor-core kernels of the forward path (impl = 2, the default).
 //
 // The round-1 kernels (tt_tc.cuh) ran every phase of a tile on the same 128 threads: gather, layer round trips and
-// the normal pass were serialised per group, and their times ADDED UP (DESIGN.md "Phase anatomy").  Here a CTA has
-// three roles that overlap through mbarrier hand-offs:
+// the normal pass were serialised per group and their times ADDED UP (DESIGN.md "Phase anatomy").  Here a CTA has a
+// dedicated memory warpgroup and two consumer groups that overlap through mbarrier hand-offs:
 //
-//   gather warps (threads 0..127, "M group")   compute the sample positions and the bilinear tap tables of a 128-point
-//                                              tile, gather the texels cooperatively (consecutive lanes = consecutive
-//                                              16-byte chunks of a channel-last texel, 24 loads in flight per lane) and
-//                                              write BLENDED rows into a shared-memory stage; they run ahead of the
-//                                              consumers by up to two stage buffers per consumer group
-//   2 consumer groups (2 x 128 threads)        thread = stage row = TMEM lane: row -> tf32 hi/lo split -> TMEM A operand,
-//                                              one elected thread issues the tcgen05.mma of a layer (3xTF32), the
-//                                              epilogue reads the accumulator back in 32-column halves (ReLU / masks /
-//                                              split), second layer, head.  The two groups alternate chunks, so one
-//                                              group's epilogue overlaps the other's MMAs.
+//   gather warps (threads 0..127, "M group")   for each consumer group in turn: sample positions + bilinear tap tables of
+//                                              the group's next 128-point tile, cooperative gather of the blended encoding
+//                                              (consecutive lanes = consecutive 16-byte chunks of a channel-last texel,
+//                                              24 loads in flight per lane) into the group's stage; and, when a group has
+//                                              produced d sdf / d enc, the normal pass: second cooperative pass over the 12
+//                                              taps (4 lanes per point) -> d sdf / d x
+//   2 consumer groups (2 x 128 threads)        thread = sample point = TMEM lane: the decoder layers on tcgen05 (3xTF32, A
+//                                              operand in TMEM, accumulator read back in 32-column halves to keep the
+//                                              register count at 168), heads, outputs.
+// While one group runs its layers the gather warps serve the other group, so the load path and the tensor pipe are busy
+// at the same time (round 1: `mem_lock` spin lock between two groups that each did their own gathers).
 //
-// Analytic normal without a second gather: instead of the adjoint pass (de = W1ᵀ(m1 ⊙ W2ᵀ(m2 ⊙ w3)) followed by a second
-// pass over the 12 taps), the gather warps also blend the three TANGENT vectors  V_a = ∂e/∂x_a  (same 12 texels, tap
-// coefficients ∂w_t/∂x_a), and a chunk is 32 points x 4 rows (e, V_x, V_y, V_z).  The tangent rows run through the
-// same two layers with the ReLU masks of their point's primal row (one warp shuffle: the 4 rows of a point are 4
-// adjacent lanes), and  ∂sdf/∂x_a = Σ_j m2_j w3_j (W2 (m1 ⊙ W1 V_a))_j  comes out of the same epilogue as the SDF.
-// That removes the second gather (41 of the 137 ms of the round-1 fine pass at config 2), both transposed weight tiles
-// (-48 KB of shared memory, which the L1 cache gets back) and two of the four dependent layer round trips per point.
-//
-// TMA note: a cp.async.bulk.tensor producer (one 2x2xC box per point and plane, hardware zero fill = zeros padding) was
-// measured and is NOT used: box issue costs ~67 cycles per box and warp (tools/tma_gather_probe.cu,
-// profiles/r02_tma_gather_probe.txt: 2.1-4.1 TB/s against 9.8-19 TB/s for the cooperative LDG gather with 4-12 warps).
+// Measured alternatives that are NOT used:
+//   * TMA producer (cp.async.bulk.tensor 2x2xC boxes, hardware zero fill = zeros padding): box issue costs ~67 cycles per
+//     box and warp; 2.1-4.1 TB/s against 9.8-19 TB/s for the cooperative LDG gather (tools/tma_gather_probe.cu).
+//   * tangent-mode normal (rows e, de/dx, de/dy, de/dz through two layers, no second gather, no transposed weights):
+//     parity-green but 2x the epilogue rows and MMAs per point; the kernel is issue-bound and ran 20 % SLOWER than round 1
+//     (profiles/r02_ws_tangent_*.txt).
 #pragma once
 #include "tt_tc.cuh"
 
 namespace tt {
 
+// Optional phase anatomy (-DTT_WS_TIMING): thread 0 of the gather warps and thread 0 of consumer group 0 of CTA 0 accumulate
+// the cycles they spend in each phase into g_ws_prof (read back with tt_debug_ws_prof).
+#if defined(TT_WS_TIMING) && !defined(TT_EMUL)
+__device__ unsigned long long g_ws_prof[32];
+__device__ __forceinline__ void g_ws_prof_tiles() { g_ws_prof[16] += 1; }
+#define WS_T0(var) long long var = clock64()
+#define WS_ACC(slot, var, cond) do { if (cond) { const long long n_ = clock64(); g_ws_prof[slot] += (unsigned long long)(n_ - var); var = n_; } } while (0)
+#else
+__device__ __forceinline__ void g_ws_prof_tiles() {}
+#define WS_T0(var)
+#define WS_ACC(slot, var, cond)
+#endif
+
 constexpr int WS_M = 128;                               // gather threads
 constexpr int WS_CG = 2;                                // consumer groups
 constexpr int WS_THREADS = WS_M + WS_CG * TC_GROUP;     // 384
-constexpr int WS_NBUF = 2;                              // stage buffers per consumer group
-
-template <int C, bool NORMAL>
-struct GeoWs {
-    static constexpr int SP = C + 4;
-    static constexpr int NK = NORMAL ? 4 : 1;           // stage rows per point: e (+ V_x, V_y, V_z)
-    static constexpr int PTS = TC_GROUP / NK;           // points per chunk (= 128 stage rows)
-    static constexpr int NCOEF = NORMAL ? 3 : 1;        // coefficient tables per tap: w (+ dw/dix, dw/diy)
-    // float offsets
-    static constexpr int W1H = 0, W1L = W1H + 64 * C, W2H = W1L + 64 * C, W2L = W2H + 4096, W3 = W2L + 4096;
-    static constexpr int MTAB = W3 + 64;                // gather-group tables of one 128-point tile
-    static constexpr int TAP_O = 0, TAP_W = TAP_O + 128 * 12, TAP_CX = TAP_W + 128 * 12;
-    static constexpr int TAP_CY = TAP_CX + (NORMAL ? 128 * 12 : 0), PBASE = TAP_CY + (NORMAL ? 128 * 12 : 0);
-    static constexpr int MMETA = PBASE + 128, MTAB_FLOATS = MMETA + 128 * 4;
-    static constexpr int STAGE0 = MTAB + MTAB_FLOATS;
-    static constexpr int ROWS = 0, META = ROWS + 128 * SP, STAGE_FLOATS = META + PTS * 4;
-    static constexpr int NSTAGE = WS_CG * WS_NBUF;
-    static constexpr int BARS = STAGE0 + NSTAGE * STAGE_FLOATS;        // uint64: full[NSTAGE], empty[NSTAGE], mma[WS_CG]
-    static constexpr int TOTAL = BARS + 2 * (2 * NSTAGE + WS_CG) + 4;
-    static_assert(BARS % 2 == 0, "mbarriers must be 8-byte aligned");
-};
-
-// ---- gather of one chunk -------------------------------------------------------------------------------------------------
-// item = (point, 16-byte channel chunk); thread mt takes items mt, mt + 128, ...  JB items per batch so that 12 * JB
-// independent 16-byte loads are in flight per lane.  p0 = first point of the chunk inside the tile's tables.
-template <int C, bool NORMAL>
-__device__ __forceinline__ void ws_gather_chunk(const float* __restrict__ planes, size_t ps, const int* tap_o,
-                                                const float* tap_w, const float* tap_cx, const float* tap_cy,
-                                                const uint32_t* pbase, int p0, float* rows, int mt) {
-    using L = GeoWs<C, NORMAL>;
-    constexpr int U = C / 4, SP = C + 4, JB = 2, ITEMS = L::PTS * U;
-#pragma unroll 1
-    for (int i0 = mt; i0 < ITEMS; i0 += JB * WS_M) {
-        float4 v[JB][12];
-        int pt[JB], ch[JB];
-#pragma unroll
-        for (int b = 0; b < JB; ++b) {
-            const int item = i0 + b * WS_M < ITEMS ? i0 + b * WS_M : ITEMS - 1;      // tail: repeat the last item (not stored)
-            pt[b] = item / U; ch[b] = item - pt[b] * U;
-            const int P = p0 + pt[b];
-            const float* base = planes + (size_t)pbase[P] * 6 * ps + ch[b] * 4;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int4 o4 = *reinterpret_cast<const int4*>(tap_o + P * 12 + k * 4);
-                const float* pb = base + (size_t)k * ps;
-                v[b][k * 4 + 0] = ldg4(pb + (size_t)o4.x * C); v[b][k * 4 + 1] = ldg4(pb + (size_t)o4.y * C);
-                v[b][k * 4 + 2] = ldg4(pb + (size_t)o4.z * C); v[b][k * 4 + 3] = ldg4(pb + (size_t)o4.w * C);
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < JB; ++b) {
-            if (i0 + b * WS_M >= ITEMS) continue;
-            const int P = p0 + pt[b];
-            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 V[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) V[a] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float4 w4 = *reinterpret_cast<const float4*>(tap_w + P * 12 + k * 4);
-                const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
-                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const float4 q = v[b][k * 4 + t];
-                    s.x = fmaf(ww[t], q.x, s.x); s.y = fmaf(ww[t], q.y, s.y); s.z = fmaf(ww[t], q.z, s.z); s.w = fmaf(ww[t], q.w, s.w);
-                }
-                e.x += s.x; e.y += s.y; e.z += s.z; e.w += s.w;
-                if (NORMAL) {
-                    const float4 x4 = *reinterpret_cast<const float4*>(tap_cx + P * 12 + k * 4);
-                    const float4 y4 = *reinterpret_cast<const float4*>(tap_cy + P * 12 + k * 4);
-                    const float cx[4] = {x4.x, x4.y, x4.z, x4.w}, cy[4] = {y4.x, y4.y, y4.z, y4.w};
-                    const int ax = k == 2 ? 2 : 0, ay = k == 1 ? 2 : 1;          // plane_ax / plane_ay, compile time
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const float4 q = v[b][k * 4 + t];
-                        V[ax].x = fmaf(cx[t], q.x, V[ax].x); V[ax].y = fmaf(cx[t], q.y, V[ax].y);
-                        V[ax].z = fmaf(cx[t], q.z, V[ax].z); V[ax].w = fmaf(cx[t], q.w, V[ax].w);
-                        V[ay].x = fmaf(cy[t], q.x, V[ay].x); V[ay].y = fmaf(cy[t], q.y, V[ay].y);
-                        V[ay].z = fmaf(cy[t], q.z, V[ay].z); V[ay].w = fmaf(cy[t], q.w, V[ay].w);
-                    }
-                }
-            }
-            float* r = rows + (size_t)(pt[b] * L::NK) * SP + ch[b] * 4;
-            *reinterpret_cast<float4*>(r) = e;
-            if (NORMAL) {
-                *reinterpret_cast<float4*>(r + SP) = V[0];
-                *reinterpret_cast<float4*>(r + 2 * SP) = V[1];
-                *reinterpret_cast<float4*>(r + 3 * SP) = V[2];
-            }
-        }
-    }
+constexpr int WS_NBUF = 2;                              // stage buffers per consumer group (colour kernel)
+// Register re-balancing between the roles (setmaxnreg works per warpgroup = 4 consecutive warps): the kernel starts with
+// 65536 / 384 -> 168 registers per thread; the gather warpgroup grows to WS_REG_M (more loads in flight: the gather is
+// bound by loads in flight, tools/tma_gather_probe.cu), the two consumer warpgroups shrink to WS_REG_C.
+// 128 * 232 + 256 * 136 = 64512 = 384 * 168.
+#ifndef WS_REG_M
+#define WS_REG_M 232
+#define WS_REG_C 136
+#endif
+#ifndef WS_GATHER_JB
+#define WS_GATHER_JB 3          // items (12 loads each) in flight per gather lane
+#endif
+template <int N> __device__ __forceinline__ void ws_reg_inc() {
+#ifndef TT_EMUL
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+#endif
+}
+template <int N> __device__ __forceinline__ void ws_reg_dec() {
+#ifndef TT_EMUL
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+#endif
 }
 
 // 32 accumulator columns -> registers
@@ -148,36 +86,129 @@ __device__ __forceinline__ void ws_st32_split(const Umma& u, uint32_t col, const
     tmem_st32(u.tmem + u.lane_base + TC_COL_AHI + col, hi);
     tmem_st32(u.tmem + u.lane_base + TC_COL_ALO + col, lo);
 }
+// bit j = (d[j] > 0).  relu first (one FMNMX, +0 for anything <= 0), then the sign of the negated bit pattern
 __device__ __forceinline__ uint32_t ws_pos_bits(const float (&d)[32]) {
     uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) m |= (d[j] > 0.f ? 1u : 0u) << j;
+    for (int j = 31; j >= 0; --j) {
+        const uint32_t neg = 0u - __float_as_uint(fmaxf(d[j], 0.f));      // top bit set iff d[j] > 0
+        m = (m << 1) | (neg >> 31);
+    }
     return m;
 }
-__device__ __forceinline__ uint32_t ws_shfl_u32(uint32_t v, int src_lane) {
-    return (uint32_t)__shfl_sync(0xffffffffu, (int)v, src_lane);
+// all-ones / all-zeros word from bit j of m
+__device__ __forceinline__ uint32_t ws_bit_mask(uint32_t m, int j) { return 0u - ((m >> j) & 1u); }
+
+template <int C, bool NORMAL>
+struct GeoWs {
+    static constexpr int SP = C + 4, CP = (C + 15) / 16 * 16, U = C / 4;
+    // float offsets: weight tiles (tf32 hi / lo, canonical K-major)
+    static constexpr int W1H = 0, W1L = W1H + 64 * C, W2H = W1L + 64 * C, W2L = W2H + 4096;
+    static constexpr int W2TH = W2L + 4096, W2TL = W2TH + (NORMAL ? 4096 : 0);
+    static constexpr int W1TH = W2TL + (NORMAL ? 4096 : 0), W1TL = W1TH + (NORMAL ? CP * 64 : 0);
+    static constexpr int W3 = W1TL + (NORMAL ? CP * 64 : 0);
+    // gather-group tables of the tile being gathered
+    static constexpr int MTAB = W3 + 64;
+    static constexpr int TAP_O = 0, TAP_W = TAP_O + 128 * 12, TAP_CX = TAP_W + 128 * 12;
+    static constexpr int TAP_CY = TAP_CX + (NORMAL ? 128 * 12 : 0), PBASE = TAP_CY + (NORMAL ? 128 * 12 : 0);
+    static constexpr int MTAB_FLOATS = PBASE + 128;
+    // per consumer group: meta (id, x) and the blended encodings of its next tile
+    static constexpr int GROUP0 = MTAB + MTAB_FLOATS;
+    static constexpr int META = 0, STAGE = META + 128 * 4, GROUP_FLOATS = STAGE + 128 * SP;
+    static constexpr int BARS = GROUP0 + WS_CG * GROUP_FLOATS;     // uint64: full, stage_free, mma per group
+    static constexpr int TOTAL = BARS + 2 * 3 * WS_CG + 4;
+    static_assert(BARS % 2 == 0, "mbarriers must be 8-byte aligned");
+    // tangent rows V_a = d enc / d x_a of a tile in the L2-resident scratch: [pt / 8][a][chunk][pt % 8][4 floats]
+    // (the gather warps write 64-byte runs, the consumers read 128-byte runs)
+    static constexpr int VTILE = 128 * 3 * C;                      // floats per (group, buffer)
+    __host__ __device__ static constexpr int vidx(int pt, int a, int ch) { return ((((pt >> 3) * 3 + a) * U + ch) * 8 + (pt & 7)) * 4; }
+};
+__host__ __device__ constexpr size_t ws_vscratch_floats(int n_cta, int C) { return (size_t)n_cta * WS_CG * 2 * 128 * 3 * C; }
+
+// Sample of a gather job, prefetched one job ahead as RAW loaded words: the arithmetic that turns them into a position
+// runs one job later, so the global-load latency (sample id -> interval edges / ray) hides behind the previous gather.
+struct WsRaw { float v[8]; int id; };
+__device__ __forceinline__ int ws_load_id(const TcSrc& src, int64_t tile, int mt, int64_t n_live, int64_t n_tiles) {
+    if (tile >= n_tiles) return -1;
+    const int64_t slot = tile * TC_GROUP + mt;
+    if (slot >= n_live) return -1;
+    return src.index ? src.index[slot] : (int)slot;
+}
+__device__ __forceinline__ WsRaw ws_load_raw(const TcSrc& s, int id) {
+    WsRaw r; r.id = id;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
+    if (id < 0) return r;
+    if (s.mode == 0) {
+        r.v[0] = s.points[(int64_t)id * 3]; r.v[1] = s.points[(int64_t)id * 3 + 1]; r.v[2] = s.points[(int64_t)id * 3 + 2];
+    } else if (s.mode == 1 || s.mode == 2) {
+        int64_t ray;
+        if (s.mode == 1) {
+            ray = id / s.rs.S; const int i = id - (int)ray * s.rs.S;
+            r.v[0] = s.rs.t_starts[ray * s.rs.t_stride + i]; r.v[1] = s.rs.t_ends[ray * s.rs.t_stride + i];
+        } else {
+            ray = id / s.n_imp;
+            r.v[0] = s.jitter0 ? s.jitter0[ray] : 0.f;
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { r.v[2 + a] = s.rs.rays_o[ray * 3 + a]; r.v[5 + a] = s.rs.rays_d[ray * 3 + a]; }
+    }
+    return r;
+}
+// same arithmetic as tc_point (tt_tc.cuh), on the prefetched words
+__device__ __forceinline__ void ws_point_from_raw(const TcSrc& s, const WsRaw& r, float (&x)[3], int& prompt) {
+    x[0] = x[1] = x[2] = 0.f; prompt = 0;
+    if (r.id < 0) return;
+    if (s.mode == 0) {
+        x[0] = r.v[0]; x[1] = r.v[1]; x[2] = r.v[2];
+        prompt = (int)((int64_t)r.id / s.M);
+    } else if (s.mode == 3) {
+        const int64_t v = (int64_t)r.id % s.M; const int rr = s.grid_res;
+        x[0] = grid_coord_tc((int)(v / ((int64_t)rr * rr)), rr); x[1] = grid_coord_tc((int)((v / rr) % rr), rr);
+        x[2] = grid_coord_tc((int)(v % rr), rr);
+        prompt = (int)((int64_t)r.id / s.M);
+    } else {
+        int ray; float tm;
+        if (s.mode == 1) {
+            ray = r.id / s.rs.S;
+            tm = __fmul_rn(__fadd_rn(r.v[0], r.v[1]), 0.5f);
+        } else {
+            ray = r.id / s.n_imp; const int j = r.id - ray * s.n_imp;
+            const bool strat = s.jitter0 != nullptr; const float b = r.v[0];
+            const float t0 = stot_u(quantile_s(j, s.n_imp, strat, b), s.near_plane, s.far_plane);
+            const float t1 = stot_u(quantile_s(j + 1, s.n_imp, strat, b), s.near_plane, s.far_plane);
+            tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(r.v[2 + a], __fmul_rn(r.v[5 + a], tm));
+        prompt = ray / s.rays_per_cache;
+    }
 }
 
-// SDF decoder (+ analytic normal) at a list of points.  sources and outputs as k_geo_tc.
+// SDF decoder (+ analytic normal) at a list of points.  Sources and outputs as k_geo_tc (tt_tc.cuh); vscratch:
+// ws_vscratch_floats(gridDim.x, C) floats (NORMAL only).
 template <int C, bool NORMAL>
 __global__ void __launch_bounds__(WS_THREADS, 1) k_geo_ws(const float* __restrict__ planes, const float* __restrict__ wp,
                                                          tt_config cfg, TcSrc src, int64_t N, float* sdf_o,
                                                          float* sdf_orig_o, float* grad_o, float* normal_o,
-                                                         uint64_t* masks_o) {
+                                                         uint64_t* masks_o, float* __restrict__ vscratch) {
     TT_SHARED(smem);
     using L = GeoWs<C, NORMAL>;
-    constexpr int SP = L::SP, NK = L::NK, PTS = L::PTS;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int SP = L::SP, CP = L::CP, U = L::U;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const WOff wo = woff(C);
     btile_fill(smem + L::W1H, smem + L::W1L, 64, C, [&](int n, int k) { return __ldg(wp + wo.w1s + n * C + k); }, tid, WS_THREADS);
     btile_fill(smem + L::W2H, smem + L::W2L, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2s + n * 64 + k); }, tid, WS_THREADS);
+    if (NORMAL) {
+        btile_fill(smem + L::W2TH, smem + L::W2TL, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2s + k * 64 + n); }, tid, WS_THREADS);
+        btile_fill(smem + L::W1TH, smem + L::W1TL, CP, 64, [&](int n, int k) { return n < C ? __ldg(wp + wo.w1s + k * C + n) : 0.f; }, tid, WS_THREADS);
+    }
     if (tid < 64) smem[L::W3 + tid] = __ldg(wp + wo.w3s + tid);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BARS);
-    uint64_t* full = bars; uint64_t* empty = bars + L::NSTAGE; uint64_t* mmab = bars + 2 * L::NSTAGE;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * L::NSTAGE + WS_CG);
+    uint64_t* full = bars; uint64_t* sfree = bars + WS_CG; uint64_t* mmab = bars + 2 * WS_CG;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WS_CG);
     if (tid == 0) {
-        for (int i = 0; i < L::NSTAGE; ++i) { mbar_init_n(full + i, WS_M); mbar_init_n(empty + i, TC_GROUP); }
-        for (int g = 0; g < WS_CG; ++g) mbar_init_n(mmab + g, 1);
+        for (int g = 0; g < WS_CG; ++g) { mbar_init_n(full + g, WS_M); mbar_init_n(sfree + g, TC_GROUP); mbar_init_n(mmab + g, 1); }
         mbar_init_fence();
     }
     if (warp == 0) tmem_alloc_warp(tmem_slot, 512);
@@ -188,62 +219,140 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_geo_ws(const float* __restric
     const size_t ps = (size_t)cfg.R * cfg.R * C;
     const int64_t n_live = src.count ? (int64_t)*src.count : N;
     const int64_t n_tiles = (n_live + TC_GROUP - 1) / TC_GROUP;
+    const int64_t tile_stride = (int64_t)gridDim.x * WS_CG;
+    float* vcta = NORMAL ? vscratch + (size_t)blockIdx.x * WS_CG * 2 * L::VTILE : nullptr;
+    // job j of this CTA: consumer group j & 1, its tile number j >> 1
+    auto job_tile = [&](int64_t j) { return (int64_t)blockIdx.x * WS_CG + (j & 1) + (j >> 1) * tile_stride; };
 
     if (tid < WS_M) {
         // ============================================================================ gather warps
+        ws_reg_inc<WS_REG_M>();
         const int mt = tid;
         float* tab = smem + L::MTAB;
         int* tap_o = reinterpret_cast<int*>(tab + L::TAP_O);
         float* tap_w = tab + L::TAP_W; float* tap_cx = tab + L::TAP_CX; float* tap_cy = tab + L::TAP_CY;
         uint32_t* pbase = reinterpret_cast<uint32_t*>(tab + L::PBASE);
-        float* mmeta = tab + L::MMETA;
-        int64_t chunk = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t slot = tile * TC_GROUP + mt;
-            const bool valid = slot < n_live;
-            const int64_t id = valid ? (src.index ? (int64_t)src.index[slot] : slot) : 0;
-            float x[3] = {0.f, 0.f, 0.f}; int prompt = 0;
+        const bool prof_m = blockIdx.x == 0 && mt == 0; (void)prof_m;
+        WS_T0(tm);
+        // software pipeline over jobs: sample ids two jobs ahead, sample positions one job ahead (both are dependent
+        // global loads whose latency would otherwise be exposed once per tile)
+        WsRaw cur = ws_load_raw(src, ws_load_id(src, job_tile(0), mt, n_live, n_tiles));
+        int id_next = ws_load_id(src, job_tile(1), mt, n_live, n_tiles);
+        for (int64_t j = 0; job_tile(j) < n_tiles; ++j) {
+            const int g = (int)(j & 1);
+            const uint32_t par = (uint32_t)((j >> 1) & 1);
+            float* gs = smem + L::GROUP0 + g * L::GROUP_FLOATS;
+            const WsRaw nxt = ws_load_raw(src, id_next);                        // in flight during this job's gather
+            id_next = ws_load_id(src, job_tile(j + 2), mt, n_live, n_tiles);
+            const bool valid = cur.id >= 0;
+            float cx_[3]; int cprompt;
+            ws_point_from_raw(src, cur, cx_, cprompt);
             Taps tp[3];
-            if (valid) {
-                tc_point(src, id, x, prompt);
+            {
                 float p[3];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
+                for (int a = 0; a < 3; ++a) p[a] = rescale1(cx_[a], cfg.radius);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) tp[k] = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
+                for (int kk = 0; kk < 3; ++kk) tp[kk] = make_taps(p[plane_ax(kk)], p[plane_ay(kk)], cfg.R);
             }
+            group_sync(0);                          // every gather thread is done with the previous job's tables
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                int4 o4; float4 w4, x4, y4;
-                const bool i0 = valid && tp[k].o[0] >= 0, i1 = valid && tp[k].o[1] >= 0;
-                const bool i2 = valid && tp[k].o[2] >= 0, i3 = valid && tp[k].o[3] >= 0;
-                o4.x = i0 ? tp[k].o[0] : 0; o4.y = i1 ? tp[k].o[1] : 0; o4.z = i2 ? tp[k].o[2] : 0; o4.w = i3 ? tp[k].o[3] : 0;
-                w4.x = i0 ? tp[k].w[0] : 0.f; w4.y = i1 ? tp[k].w[1] : 0.f; w4.z = i2 ? tp[k].w[2] : 0.f; w4.w = i3 ? tp[k].w[3] : 0.f;
-                *reinterpret_cast<int4*>(tap_o + mt * 12 + k * 4) = o4;
-                *reinterpret_cast<float4*>(tap_w + mt * 12 + k * 4) = w4;
-                if (NORMAL) {      // d e / d ix = wy0 (t1 - t0) + wy1 (t3 - t2),  d e / d iy = wx0 (t2 - t0) + wx1 (t3 - t1)
-                    x4.x = i0 ? -tp[k].wy0 : 0.f; x4.y = i1 ? tp[k].wy0 : 0.f; x4.z = i2 ? -tp[k].wy1 : 0.f; x4.w = i3 ? tp[k].wy1 : 0.f;
-                    y4.x = i0 ? -tp[k].wx0 : 0.f; y4.y = i1 ? -tp[k].wx1 : 0.f; y4.z = i2 ? tp[k].wx0 : 0.f; y4.w = i3 ? tp[k].wx1 : 0.f;
-                    *reinterpret_cast<float4*>(tap_cx + mt * 12 + k * 4) = x4;
-                    *reinterpret_cast<float4*>(tap_cy + mt * 12 + k * 4) = y4;
+            for (int kk = 0; kk < 3; ++kk) {
+                int4 o4; float4 w4;
+                const bool i0 = valid && tp[kk].o[0] >= 0, i1 = valid && tp[kk].o[1] >= 0;
+                const bool i2 = valid && tp[kk].o[2] >= 0, i3 = valid && tp[kk].o[3] >= 0;
+                o4.x = i0 ? tp[kk].o[0] : 0; o4.y = i1 ? tp[kk].o[1] : 0; o4.z = i2 ? tp[kk].o[2] : 0; o4.w = i3 ? tp[kk].o[3] : 0;
+                w4.x = i0 ? tp[kk].w[0] : 0.f; w4.y = i1 ? tp[kk].w[1] : 0.f; w4.z = i2 ? tp[kk].w[2] : 0.f; w4.w = i3 ? tp[kk].w[3] : 0.f;
+                *reinterpret_cast<int4*>(tap_o + mt * 12 + kk * 4) = o4;
+                *reinterpret_cast<float4*>(tap_w + mt * 12 + kk * 4) = w4;
+                if (NORMAL) {   // d enc / d ix = wy0 (t1 - t0) + wy1 (t3 - t2),  d enc / d iy = wx0 (t2 - t0) + wx1 (t3 - t1)
+                    float4 x4, y4;
+                    x4.x = i0 ? -tp[kk].wy0 : 0.f; x4.y = i1 ? tp[kk].wy0 : 0.f; x4.z = i2 ? -tp[kk].wy1 : 0.f; x4.w = i3 ? tp[kk].wy1 : 0.f;
+                    y4.x = i0 ? -tp[kk].wx0 : 0.f; y4.y = i1 ? -tp[kk].wx1 : 0.f; y4.z = i2 ? tp[kk].wx0 : 0.f; y4.w = i3 ? tp[kk].wx1 : 0.f;
+                    *reinterpret_cast<float4*>(tap_cx + mt * 12 + kk * 4) = x4;
+                    *reinterpret_cast<float4*>(tap_cy + mt * 12 + kk * 4) = y4;
                 }
             }
-            pbase[mt] = (uint32_t)prompt;
-            *reinterpret_cast<float4*>(mmeta + mt * 4) = make_float4(__uint_as_float((uint32_t)(valid ? (int)id : -1)), x[0], x[1], x[2]);
+            pbase[mt] = (uint32_t)cprompt;
+            WS_ACC(1, tm, prof_m);
+            mbar_wait_parity(smem_u32(sfree + g), par ^ 1u);        // the group has taken its previous tile out of the stage
+            WS_ACC(0, tm, prof_m);
+            *reinterpret_cast<float4*>(gs + L::META + mt * 4) =
+                make_float4(__uint_as_float((uint32_t)cur.id), cx_[0], cx_[1], cx_[2]);
             group_sync(0);
+            // ---- cooperative gather: item = (point, 16-byte channel chunk); 2 items = 24 loads in flight per lane.
+            // Blends the encoding e (-> stage) and, for the normal, the tangent rows V_a = d e / d x_a (-> L2 scratch).
+            float* stage = gs + L::STAGE;
+            float* vt = NORMAL ? vcta + (size_t)(g * 2 + (int)par) * L::VTILE : nullptr;
+            constexpr int JB = WS_GATHER_JB, ITEMS = 128 * U;
 #pragma unroll 1
-            for (int q = 0; q < NK; ++q, ++chunk) {
-                const int sb = (int)(chunk & 1) * WS_NBUF + (int)((chunk >> 1) & 1);
-                mbar_wait_parity(smem_u32(empty + sb), (uint32_t)(((chunk >> 2) & 1) ^ 1));
-                float* st = smem + L::STAGE0 + sb * L::STAGE_FLOATS;
-                ws_gather_chunk<C, NORMAL>(planes, ps, tap_o, tap_w, tap_cx, tap_cy, pbase, q * PTS, st + L::ROWS, mt);
-                if (mt < PTS) *reinterpret_cast<float4*>(st + L::META + mt * 4) = *reinterpret_cast<const float4*>(mmeta + (q * PTS + mt) * 4);
-                mbar_arrive(smem_u32(full + sb));
+            for (int i0 = mt; i0 < ITEMS; i0 += JB * WS_M) {
+                float4 v[JB][12];
+                int pt[JB], ch[JB];
+#pragma unroll
+                for (int b = 0; b < JB; ++b) {
+                    const int item = i0 + b * WS_M < ITEMS ? i0 + b * WS_M : ITEMS - 1;      // tail: repeat the last item (not stored)
+                    pt[b] = item / U; ch[b] = item - pt[b] * U;
+                    const float* base = planes + (size_t)pbase[pt[b]] * 6 * ps + ch[b] * 4;
+#pragma unroll
+                    for (int kk = 0; kk < 3; ++kk) {
+                        const int4 o4 = *reinterpret_cast<const int4*>(tap_o + pt[b] * 12 + kk * 4);
+                        const float* pb = base + (size_t)kk * ps;
+                        v[b][kk * 4 + 0] = ldg4(pb + (size_t)o4.x * C); v[b][kk * 4 + 1] = ldg4(pb + (size_t)o4.y * C);
+                        v[b][kk * 4 + 2] = ldg4(pb + (size_t)o4.z * C); v[b][kk * 4 + 3] = ldg4(pb + (size_t)o4.w * C);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < JB; ++b) {
+                    if (i0 + b * WS_M >= ITEMS) continue;
+                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 V[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) V[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int kk = 0; kk < 3; ++kk) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(tap_w + pt[b] * 12 + kk * 4);
+                        const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+                        float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float4 q = v[b][kk * 4 + t];
+                            sacc.x = fmaf(ww[t], q.x, sacc.x); sacc.y = fmaf(ww[t], q.y, sacc.y);
+                            sacc.z = fmaf(ww[t], q.z, sacc.z); sacc.w = fmaf(ww[t], q.w, sacc.w);
+                        }
+                        e.x += sacc.x; e.y += sacc.y; e.z += sacc.z; e.w += sacc.w;
+                        if (NORMAL) {
+                            const float4 x4 = *reinterpret_cast<const float4*>(tap_cx + pt[b] * 12 + kk * 4);
+                            const float4 y4 = *reinterpret_cast<const float4*>(tap_cy + pt[b] * 12 + kk * 4);
+                            const float cx[4] = {x4.x, x4.y, x4.z, x4.w}, cy[4] = {y4.x, y4.y, y4.z, y4.w};
+                            const int ax = kk == 2 ? 2 : 0, ay = kk == 1 ? 2 : 1;          // plane_ax / plane_ay, compile time
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float4 q = v[b][kk * 4 + t];
+                                V[ax].x = fmaf(cx[t], q.x, V[ax].x); V[ax].y = fmaf(cx[t], q.y, V[ax].y);
+                                V[ax].z = fmaf(cx[t], q.z, V[ax].z); V[ax].w = fmaf(cx[t], q.w, V[ax].w);
+                                V[ay].x = fmaf(cy[t], q.x, V[ay].x); V[ay].y = fmaf(cy[t], q.y, V[ay].y);
+                                V[ay].z = fmaf(cy[t], q.z, V[ay].z); V[ay].w = fmaf(cy[t], q.w, V[ay].w);
+                            }
+                        }
+                    }
+                    *reinterpret_cast<float4*>(stage + pt[b] * SP + ch[b] * 4) = e;
+                    if (NORMAL) {
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) *reinterpret_cast<float4*>(vt + L::vidx(pt[b], a, ch[b])) = V[a];
+                    }
+                }
             }
-            group_sync(0);          // the tables are rewritten by the next tile
+#ifndef TT_EMUL
+            if (NORMAL) __threadfence_block();
+#endif
+            mbar_arrive(smem_u32(full + g));
+            WS_ACC(2, tm, prof_m);
+            cur = nxt;
         }
     } else {
         // ============================================================================ consumer groups
+        ws_reg_dec<WS_REG_C>();
         const int g = (tid - WS_M) / TC_GROUP, tg = (tid - WS_M) % TC_GROUP;
         Umma u;
         u.tmem = *tmem_slot + (uint32_t)g * TC_COLS_PER_GROUP;
@@ -252,90 +361,121 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_geo_ws(const float* __restric
         const bool leader = tg == 0;
         const BTile bW1 = btile_make(smem + L::W1H, smem + L::W1L, 64, C);
         const BTile bW2 = btile_make(smem + L::W2H, smem + L::W2L, 64, 64);
+        const BTile bW2T = btile_make(smem + L::W2TH, smem + L::W2TL, 64, 64);
+        const BTile bW1T = btile_make(smem + L::W1TH, smem + L::W1TL, CP, 64);
         const float* w3 = smem + L::W3;
-        const int prim = lane & ~3;                     // lane of this point's primal row (NORMAL)
-        int64_t chunk = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-#pragma unroll 1
-            for (int q = 0; q < NK; ++q, ++chunk) {
-                if ((int)(chunk & 1) != g) continue;
-                const int sb = g * WS_NBUF + (int)((chunk >> 1) & 1);
-                mbar_wait_parity(smem_u32(full + sb), (uint32_t)((chunk >> 2) & 1));
-                const float* st = smem + L::STAGE0 + sb * L::STAGE_FLOATS;
-                const float4 mv = *reinterpret_cast<const float4*>(st + L::META + (NORMAL ? (tg >> 2) : tg) * 4);
-                {
-                    float e[C];
+        float* gs = smem + L::GROUP0 + g * L::GROUP_FLOATS;
+        const float* stage = gs + L::STAGE;
+        int64_t k = 0;
+        const bool prof_c = blockIdx.x == 0 && g == 0 && tg == 0; (void)prof_c;
+        WS_T0(tc);
+        for (int64_t tile = (int64_t)blockIdx.x * WS_CG + g; tile < n_tiles; tile += tile_stride, ++k) {
+            const uint32_t par = (uint32_t)(k & 1);
+            WS_ACC(15, tc, prof_c);
+            mbar_wait_parity(smem_u32(full + g), par);
+            WS_ACC(8, tc, prof_c);
+            if (prof_c) { g_ws_prof_tiles(); }
+            const float4 mv = *reinterpret_cast<const float4*>(gs + L::META + tg * 4);
+            const int id32 = (int)__float_as_uint(mv.x);
+            const int64_t id = id32;
+            {
+                float e[C];
 #pragma unroll
-                    for (int c = 0; c < C; c += 4) {
-                        const float4 v = *reinterpret_cast<const float4*>(st + L::ROWS + tg * SP + c);
-                        e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
-                    }
-                    umma_put_A<C>(u, e);
+                for (int c = 0; c < C; c += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(stage + tg * SP + c);
+                    e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
                 }
-                mbar_arrive(smem_u32(empty + sb));      // row and meta are in registers / TMEM: the buffer is free
+                umma_put_A<C>(u, e);
+            }
+            mbar_arrive(smem_u32(sfree + g));       // row and meta are in registers / TMEM: the gather warps may refill the stage
+            group_sync(u.group);
+            if (leader) { umma_mma<3>(u, bW1, C, false); umma_commit(u); }
+            umma_wait(u);
+            uint32_t m1[2], m2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {           // h1 = relu(W1 e)
+                float d[32];
+                ws_ld32(u, TC_COL_D + 32 * h, d);
+                m1[h] = ws_pos_bits(d);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) d[j] = fmaxf(d[j], 0.f);
+                ws_st32_split(u, 32 * h, d);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            group_sync(u.group);
+            if (leader) { umma_mma<3>(u, bW2, 64, false); umma_commit(u); }
+            umma_wait(u);
+            float s = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {           // sdf = w3 . relu(W2 h1); a2 = m2 ⊙ w3 is the next A operand
+                float d[32];
+                ws_ld32(u, TC_COL_D + 32 * h, d);
+                m2[h] = ws_pos_bits(d);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s = fmaf(fmaxf(d[j], 0.f), w3[32 * h + j], s);
+                if (NORMAL) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(__float_as_uint(w3[32 * h + j]) & ws_bit_mask(m2[h], j));
+                    ws_st32_split(u, 32 * h, d);
+                }
+            }
+            const float nrm = sqrtf(mv.y * mv.y + mv.z * mv.z + mv.w * mv.w);
+            if (id32 >= 0) {
+                if (sdf_orig_o) sdf_orig_o[id] = s;
+                if (sdf_o) sdf_o[id] = s + (nrm - cfg.sdf_bias_radius);
+                if (masks_o) {     // ReLU masks for the backward
+                    masks_o[id * 4 + 2] = (uint64_t)m1[0] | ((uint64_t)m1[1] << 32);
+                    masks_o[id * 4 + 3] = (uint64_t)m2[0] | ((uint64_t)m2[1] << 32);
+                }
+            }
+            if (NORMAL) {       // unit-seed adjoint: a1 = m1 ⊙ (W2ᵀ a2), de = W1ᵀ a1;  d sdf / d x_a = de . V_a
+                tmem_wait_st();
+                tc_fence_before();
                 group_sync(u.group);
-                if (leader) { umma_mma<3>(u, bW1, C, false); umma_commit(u); }
+                if (leader) { umma_mma<3>(u, bW2T, 64, false); umma_commit(u); }
                 umma_wait(u);
-                // ---- layer-1 epilogue: ReLU (primal row) / mask (tangent rows), split, second-layer operand
-                uint32_t m1[2], m2[2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float d[32];
                     ws_ld32(u, TC_COL_D + 32 * h, d);
-                    uint32_t bits = ws_pos_bits(d);
-                    if (NORMAL) bits = ws_shfl_u32(bits, prim);
-                    m1[h] = bits;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) d[j] = ((bits >> j) & 1u) ? d[j] : 0.f;
+                    for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(__float_as_uint(d[j]) & ws_bit_mask(m1[h], j));
                     ws_st32_split(u, 32 * h, d);
                 }
                 tmem_wait_st();
                 tc_fence_before();
                 group_sync(u.group);
-                if (leader) { umma_mma<3>(u, bW2, 64, false); umma_commit(u); }
+                if (leader) { umma_mma<3>(u, bW1T, 64, false); umma_commit(u); }
                 umma_wait(u);
-                // ---- layer-2 epilogue + head: primal row -> sdf, tangent row a -> d sdf / d x_a (before the index scale)
-                float val = 0.f;
+                float de[CP];
+                umma_get_D<CP>(u, de);
+                const float* vt = vcta + (size_t)(g * 2 + (int)par) * L::VTILE;
+                float gm[3];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float d[32];
-                    ws_ld32(u, TC_COL_D + 32 * h, d);
-                    uint32_t bits = ws_pos_bits(d);
-                    if (NORMAL) bits = ws_shfl_u32(bits, prim);
-                    m2[h] = bits;
+                for (int a = 0; a < 3; ++a) {
+                    float acc = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) val = fmaf(((bits >> j) & 1u) ? d[j] : 0.f, w3[32 * h + j], val);
+                    for (int c4 = 0; c4 < U; ++c4) {
+                        const float4 q = *reinterpret_cast<const float4*>(vt + L::vidx(tg, a, c4));
+                        acc = fmaf(de[c4 * 4], q.x, fmaf(de[c4 * 4 + 1], q.y, fmaf(de[c4 * 4 + 2], q.z, fmaf(de[c4 * 4 + 3], q.w, acc))));
+                    }
+                    gm[a] = acc;
                 }
+                if (id32 >= 0 && (grad_o || normal_o)) {
+                    const float scale = 0.5f * (float)cfg.R / cfg.radius;
+                    const float inv = nrm > 0.f ? 1.f / nrm : 0.f;
+                    const float gr[3] = {gm[0] * scale + mv.y * inv, gm[1] * scale + mv.z * inv, gm[2] * scale + mv.w * inv};
+                    if (grad_o) { grad_o[id * 3] = gr[0]; grad_o[id * 3 + 1] = gr[1]; grad_o[id * 3 + 2] = gr[2]; }
+                    if (normal_o) {
+                        float n[3], len; normalize3(gr, n, len);
+                        normal_o[id * 3] = n[0]; normal_o[id * 3 + 1] = n[1]; normal_o[id * 3 + 2] = n[2];
+                    }
+                }
+            } else {
                 tc_fence_before();
-                float tx = 0.f, ty = 0.f, tz = 0.f;
-                if (NORMAL) {
-                    tx = __shfl_sync(0xffffffffu, val, prim + 1);
-                    ty = __shfl_sync(0xffffffffu, val, prim + 2);
-                    tz = __shfl_sync(0xffffffffu, val, prim + 3);
-                }
-                const int id32 = (int)__float_as_uint(mv.x);
-                if (id32 >= 0 && (!NORMAL || (lane & 3) == 0)) {
-                    const int64_t id = id32;
-                    const float x[3] = {mv.y, mv.z, mv.w};
-                    const float nrm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-                    if (sdf_orig_o) sdf_orig_o[id] = val;
-                    if (sdf_o) sdf_o[id] = val + (nrm - cfg.sdf_bias_radius);
-                    if (masks_o) {     // ReLU masks for the backward
-                        masks_o[id * 4 + 2] = (uint64_t)m1[0] | ((uint64_t)m1[1] << 32);
-                        masks_o[id * 4 + 3] = (uint64_t)m2[0] | ((uint64_t)m2[1] << 32);
-                    }
-                    if (NORMAL && (grad_o || normal_o)) {
-                        const float scale = 0.5f * (float)cfg.R / cfg.radius;
-                        const float inv = nrm > 0.f ? 1.f / nrm : 0.f;
-                        const float gr[3] = {tx * scale + x[0] * inv, ty * scale + x[1] * inv, tz * scale + x[2] * inv};
-                        if (grad_o) { grad_o[id * 3] = gr[0]; grad_o[id * 3 + 1] = gr[1]; grad_o[id * 3 + 2] = gr[2]; }
-                        if (normal_o) {
-                            float n[3], len; normalize3(gr, n, len);
-                            normal_o[id * 3] = n[0]; normal_o[id * 3 + 1] = n[1]; normal_o[id * 3 + 2] = n[2];
-                        }
-                    }
-                }
             }
+            WS_ACC(9, tc, prof_c);
         }
     }
     tc_fence_before();
