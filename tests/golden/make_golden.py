@@ -33,7 +33,8 @@ class ConstBackground(ns.background_base.BaseBackground):
         return self.color.to(dirs).reshape(*dirs.shape[:-1], 3)
 
 
-def build(C, n_samples, n_imp, normal_direction="camera", rgb_grad_shrink=1.0, seed=1):
+def build(C, n_samples, n_imp, normal_direction="camera", rgb_grad_shrink=1.0, seed=1, trainable_variance=False,
+          update_step=(0, 0)):
     torch.manual_seed(seed)
     geometry = ns.geometry.StableDiffusionTriplaneDualAttention(dict(
         radius=1.0, normal_type="analytic", sdf_bias="sphere", sdf_bias_params=0.5, rotate_planes="v1",
@@ -43,12 +44,12 @@ def build(C, n_samples, n_imp, normal_direction="camera", rgb_grad_shrink=1.0, s
                                               requires_normal=True))
     background = ConstBackground({})
     renderer = ns.renderer.GenerativeSpaceSDFVolumeRenderer(dict(
-        radius=1.0, use_volsdf=False, trainable_variance=False, learned_variance_init=0.4605,
+        radius=1.0, use_volsdf=False, trainable_variance=trainable_variance, learned_variance_init=0.4605,
         rgb_grad_shrink=rgb_grad_shrink, estimator="importance", num_samples_per_ray=n_samples,
         num_samples_per_ray_importance=n_imp, near_plane=0.1, far_plane=4.0, train_chunk_size=0,
         randomized=False, normal_direction=normal_direction, eval_chunk_size=500),
         geometry=geometry, material=material, background=background)
-    renderer.update_step(0, 0)
+    renderer.update_step(*update_step)
     # decoder weights a bit larger than nn.Linear's default so that the SDF crosses zero in the volume
     with torch.no_grad():
         for net in (geometry.sdf_network, geometry.feature_network, geometry.deformation_network):
@@ -124,8 +125,12 @@ def case_geometry(name, C, R, B, N, seed):
 
 
 def case_render(name, C, R, P, V, H, W, n_samples, n_imp, seed, training=True, normal_direction="camera",
-                rgb_grad_shrink=1.0, stratified=False, explicit_bg=False):
-    geometry, renderer, background = build(C, n_samples, n_imp, normal_direction, rgb_grad_shrink, seed=seed)
+                rgb_grad_shrink=1.0, stratified=False, explicit_bg=False, update_step=(0, 0), cos_anneal_ratio=None,
+                trainable_variance=False):
+    geometry, renderer, background = build(C, n_samples, n_imp, normal_direction, rgb_grad_shrink, seed=seed,
+                                           trainable_variance=trainable_variance, update_step=update_step)
+    if cos_anneal_ratio is not None:      # the attribute get_alpha reads (neus_volume_renderer.py:91,100-103)
+        renderer.cos_anneal_ratio = cos_anneal_ratio
     g = torch.Generator().manual_seed(seed + 200)
     B = P * V
     space_cache = (torch.randn(P, 6, C, R, R, generator=g) * 0.5).requires_grad_(True)
@@ -168,7 +173,9 @@ def case_render(name, C, R, P, V, H, W, n_samples, n_imp, seed, training=True, n
         sys.modules["threestudio.models.estimators"].importance_sampling = orig
     fix = dict(space_cache=space_cache, rays_o=rays_o, rays_d=rays_d, c2w=c2w, camera_distances=dist, bg=bg,
                meta=np.array([P, V, H, W, n_samples, n_imp, int(training), int(explicit_bg)]),
-               normal_direction=np.array(normal_direction), rgb_grad_shrink=np.array(float(renderer.rgb_grad_shrink)))
+               normal_direction=np.array(normal_direction), rgb_grad_shrink=np.array(float(renderer.rgb_grad_shrink)),
+               cos_anneal_ratio=np.array(float(renderer.cos_anneal_ratio)),
+               trainable_variance=np.array(int(trainable_variance)))
     if jit is not None:
         fix["jitter0"], fix["jitter1"] = jit
     if training:
@@ -183,7 +190,12 @@ def case_render(name, C, R, P, V, H, W, n_samples, n_imp, seed, training=True, n
         loss = sum((out[k] * cot[k]).sum() for k in cot)
         loss = loss + 0.1 * ((torch.linalg.norm(out["sdf_grad"], ord=2, dim=-1) - 1.0) ** 2).sum()  # eikonal
         params = list(geometry.sdf_network.parameters()) + list(geometry.feature_network.parameters())
+        if trainable_variance:
+            params = params + [renderer.variance._inv_std]
         grads = torch.autograd.grad(loss, [space_cache] + params)
+        if trainable_variance:
+            fix["grad_inv_std_param"] = grads[-1]
+            grads = grads[:-1]
         fix.update({"cot_" + k: v for k, v in cot.items()})
         fix["grad_space_cache"] = grads[0]
         names = [f"grad_w_sdf_{i}" for i in range(3)] + [f"grad_w_feature_{i}" for i in range(3)]
@@ -227,6 +239,12 @@ def case_patch(name, seed):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])      # optional: regenerate only the named fixtures
+    if only:
+        _cg, _cr, _cp = case_geometry, case_render, case_patch
+        case_geometry = lambda name, **k: _cg(name, **k) if name in only else None      # noqa: E731
+        case_render = lambda name, **k: _cr(name, **k) if name in only else None        # noqa: E731
+        case_patch = lambda name, **k: _cp(name, **k) if name in only else None         # noqa: E731
     case_geometry("geometry_c8_r16", C=8, R=16, B=2, N=257, seed=11)
     case_geometry("geometry_c32_r16", C=32, R=16, B=1, N=128, seed=12)
     case_render("render_train_c8", C=8, R=16, P=2, V=2, H=5, W=6, n_samples=16, n_imp=32, seed=21)
@@ -239,3 +257,10 @@ if __name__ == "__main__":
     case_render("render_eval_c8", C=8, R=16, P=1, V=3, H=4, W=5, n_samples=16, n_imp=32, seed=25,
                 training=False, explicit_bg=True)
     case_patch("patch_c8", seed=26)
+    # round 2: the parameters the shipped YAML actually trains with
+    case_render("render_train_shrink", C=8, R=16, P=1, V=2, H=4, W=5, n_samples=16, n_imp=32, seed=27,
+                rgb_grad_shrink=[0, 1, 0.01, 20000], update_step=(0, 14000))          # s = 0.307 (yaml:139)
+    case_render("render_train_cos_anneal", C=8, R=16, P=1, V=2, H=4, W=4, n_samples=8, n_imp=16, seed=28,
+                cos_anneal_ratio=0.4)
+    case_render("render_train_variance", C=8, R=16, P=1, V=2, H=4, W=4, n_samples=16, n_imp=32, seed=29,
+                trainable_variance=True)                                               # yaml:135-137 default of the class

@@ -121,8 +121,9 @@ def _cfg_for(em, fx):
     P, V, H, W, ns, nimp = [int(v) for v in fx["meta"][:6]]
     C_, R = fx["space_cache"].shape[2], fx["space_cache"].shape[3]
     pc = rp.PathConfig(num_samples_per_ray=ns, num_samples_per_ray_importance=nimp,
-                       normal_direction=fx["normal_direction"], rgb_grad_shrink=float(fx["rgb_grad_shrink"]))
-    cfg = em.config(C_, R, P, rays_per_cache=V * H * W, step=pc.render_step_size)
+                       normal_direction=fx["normal_direction"], rgb_grad_shrink=float(fx["rgb_grad_shrink"]),
+                       cos_anneal_ratio=float(fx.get("cos_anneal_ratio", 1.0)))
+    cfg = em.config(C_, R, P, rays_per_cache=V * H * W, step=pc.render_step_size, car=pc.cos_anneal_ratio)
     return cfg, pc, (P, V, H, W, ns, nimp)
 
 
@@ -148,7 +149,8 @@ def test_importance_sampler_stratified(em):
     assert_intervals_close(t, torch.cat([fx["t_starts"], fx["t_ends"][:, -1:]], 1), tv.double(), cdf.double())
 
 
-@pytest.mark.parametrize("name", ["render_train_c8", "render_train_c32", "render_train_front"])
+@pytest.mark.parametrize("name", ["render_train_c8", "render_train_c32", "render_train_front", "render_train_shrink",
+                                  "render_train_cos_anneal", "render_train_variance"])
 def test_render_forward_backward(em, name):
     fx = load_golden(name)
     cfg, pc, (P, V, H, W, ns, nimp) = _cfg_for(em, fx)
@@ -180,12 +182,16 @@ def test_render_forward_backward(em, name):
     else:                              # ... or through the per-sample sdf_grad output, like the reference's system
         g_sdf_grad = (0.1 * 2.0 * (nrm - 1.0) * sg / nrm).numpy()
     g_acc, = torch.autograd.grad(loss, acc)
-    gplanes, gw, _ = em.render_bwd(planes, wp, cfg, o, d, fx["t_starts"].numpy(), fx["t_ends"].numpy(), fwd,
-                                   g_acc.numpy(), g_sdf_grad=g_sdf_grad, rgb_scale=pc.rgb_grad_shrink)
+    gplanes, gw, gis = em.render_bwd(planes, wp, cfg, o, d, fx["t_starts"].numpy(), fx["t_ends"].numpy(), fwd,
+                                     g_acc.numpy(), g_sdf_grad=g_sdf_grad, rgb_scale=pc.rgb_grad_shrink)
     assert rel_err(torch.from_numpy(em.repack_bwd(gplanes)), fx["grad_space_cache"]) < GTOL
     names = [f"grad_w_sdf_{i}" for i in range(3)] + [f"grad_w_feature_{i}" for i in range(3)]
     for n, g in zip(names, gw):
         assert rel_err(torch.from_numpy(g), fx[n]) < GTOL, n
+    if name == "render_train_variance":     # d loss / d p with inv_std = exp(10 p): chain rule on the kernel's d loss / d inv_std
+        want = float(fx["grad_inv_std_param"])
+        got = gis * 10.0 * cfg.inv_std
+        assert abs(got - want) < GTOL * max(1.0, abs(want)), (got, want)
 
 
 def test_inv_std_gradient(em):

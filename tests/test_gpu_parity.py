@@ -85,7 +85,9 @@ def test_forward_field_grid_matches_oracle_vertex_order():
 def _renderer_for(fx):
     P, V, H, W, ns, nimp = [int(v) for v in fx["meta"][:6]]
     geom, rend = build_plugins(fx, DEV, ns, nimp, normal_direction=fx["normal_direction"],
-                               rgb_grad_shrink=float(fx["rgb_grad_shrink"]))
+                               rgb_grad_shrink=float(fx["rgb_grad_shrink"]),
+                               trainable_variance=bool(int(fx.get("trainable_variance", 0))))
+    rend.cos_anneal_ratio = float(fx.get("cos_anneal_ratio", 1.0))      # the attribute get_alpha reads (NEUS:91,100-103)
     return geom, rend, (P, V, H, W, ns, nimp)
 
 
@@ -96,7 +98,8 @@ def _kw(fx, P):
                 camera_distances=fx["camera_distances"], c2w=fx["c2w"])
 
 
-@pytest.mark.parametrize("name", ["render_train_c8", "render_train_c32", "render_train_front"])
+@pytest.mark.parametrize("name", ["render_train_c8", "render_train_c32", "render_train_front", "render_train_shrink",
+                                  "render_train_cos_anneal", "render_train_variance"])
 def test_renderer_training_matches_reference(name):
     fx = load_golden(name, DEV)
     geom, rend, (P, V, H, W, ns, nimp) = _renderer_for(fx)
@@ -125,11 +128,14 @@ def test_renderer_training_matches_reference(name):
     cot_keys = [k[4:] for k in fx if k.startswith("cot_")]
     loss = sum((out[k] * fx["cot_" + k]).sum() for k in cot_keys)
     loss = loss + 0.1 * ((torch.linalg.norm(out["sdf_grad"], ord=2, dim=-1) - 1.0) ** 2).sum()
-    grads = torch.autograd.grad(loss, [sc] + geom.decoder_weights())
+    var = [rend.variance._inv_std] if name == "render_train_variance" else []
+    grads = torch.autograd.grad(loss, [sc] + geom.decoder_weights() + var)
     assert rel_err(grads[0], fx["grad_space_cache"]) < GTOL
     for i in range(3):
         assert rel_err(grads[1 + i], fx[f"grad_w_sdf_{i}"]) < GTOL, i
         assert rel_err(grads[4 + i], fx[f"grad_w_feature_{i}"]) < GTOL, i
+    if var:         # trainable NeuS variance (the class default, REN:53): d loss / d p through inv_std = exp(10 p)
+        assert rel_err(grads[7], fx["grad_inv_std_param"]) < GTOL
 
 
 def test_renderer_stratified_matches_reference():

@@ -44,7 +44,8 @@ def test_geometry_matches_reference(name):
 def _render(fx, training=True, jitters=None):
     P, V, H, W, ns, nimp = [int(v) for v in fx["meta"][:6]]
     cfg = rp.PathConfig(num_samples_per_ray=ns, num_samples_per_ray_importance=nimp,
-                        normal_direction=fx["normal_direction"], rgb_grad_shrink=float(fx["rgb_grad_shrink"]))
+                        normal_direction=fx["normal_direction"], rgb_grad_shrink=float(fx["rgb_grad_shrink"]),
+                        cos_anneal_ratio=float(fx.get("cos_anneal_ratio", 1.0)))
     w = weights_from(fx)
     explicit_bg = bool(fx["meta"][7])
     bg = torch.ones(3) if explicit_bg else fx["bg"]
@@ -57,10 +58,19 @@ def _render(fx, training=True, jitters=None):
     return cfg, w, sc, bg, t0, t1
 
 
-@pytest.mark.parametrize("name", ["render_train_c8", "render_train_c32", "render_train_front"])
+@pytest.mark.parametrize("name", ["render_train_c8", "render_train_c32", "render_train_front", "render_train_shrink",
+                                  "render_train_cos_anneal", "render_train_variance"])
 def test_render_training_matches_reference(name):
     fx = load_golden(name)
     cfg, w, sc, bg, _, _ = _render(fx)
+    if name == "render_train_shrink":
+        assert abs(cfg.rgb_grad_shrink - 0.307) < 1e-6          # C([0,1,0.01,20000]) at step 14000 (yaml:139)
+    if name == "render_train_cos_anneal":
+        assert cfg.cos_anneal_ratio == pytest.approx(0.4)
+    var_p = None
+    if name == "render_train_variance":     # LearnedVariance parameter p with inv_std = exp(10 p) (REN:24-35)
+        var_p = torch.tensor(cfg.learned_variance_init, requires_grad=True)
+        cfg.learned_variance_init = var_p
     sc.requires_grad_(True)
     for ws in w.values():
         for t in ws:
@@ -84,11 +94,13 @@ def test_render_training_matches_reference(name):
     cot_keys = [k[4:] for k in fx if k.startswith("cot_")]
     loss = sum((out[k] * fx["cot_" + k]).sum() for k in cot_keys)
     loss = loss + 0.1 * ((torch.linalg.norm(out["sdf_grad"], ord=2, dim=-1) - 1.0) ** 2).sum()
-    grads = torch.autograd.grad(loss, [sc] + w["sdf"] + w["feature"])
+    grads = torch.autograd.grad(loss, [sc] + w["sdf"] + w["feature"] + ([var_p] if var_p is not None else []))
     assert rel_err(grads[0], fx["grad_space_cache"]) < GTOL
     for i in range(3):
         assert rel_err(grads[1 + i], fx[f"grad_w_sdf_{i}"]) < GTOL
         assert rel_err(grads[4 + i], fx[f"grad_w_feature_{i}"]) < GTOL
+    if var_p is not None:
+        assert rel_err(grads[7], fx["grad_inv_std_param"]) < GTOL
 
 
 def test_render_stratified_matches_reference():
