@@ -12,7 +12,7 @@ prompts shard across ranks with no data-path collective, weak scaling):
     config1            configs[0]: 64^2 x 32ch, 1 camera 128^2
     config4            configs[3] render part: 4 parts x PatchRenderer (global 42^2 + patch 40^2, P=2, V=4, drop-in outputs)
                        + the mesh path's 128^3 field query with gradients; the SD generator is replaced by synthetic triplanes
-    config3q           a quarter of config3 (profiling only)
+    config3q, config2q a quarter of the rays of config3 / config2 (profiling only: 4x shorter ncu replays)
 Operator workloads (a step = one call; metric named in the line): sampler, compositor, config5 (512^3 field query).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how `roofline`, `dropin` and `cpu_baseline` are defined.
@@ -36,6 +36,7 @@ WORKLOADS = {
     "config2": dict(P=4, V=4, H=256, W=256, R=256, C=40, ns=96, nimp=192),
     "config1": dict(P=1, V=1, H=128, W=128, R=64, C=32, ns=64, nimp=128),
     "config3q": dict(P=4, V=4, H=256, W=256, R=256, C=32, ns=64, nimp=128),
+    "config2q": dict(P=4, V=4, H=128, W=128, R=256, C=40, ns=96, nimp=192),
     # PRD step: the renderer is entered through the PatchRenderer with 168^2 rays per view: 42^2 global + 40^2 patch
     "config4": dict(P=2, V=4, H=168, W=168, R=256, C=32, ns=64, nimp=128, parts=4, patch=40, downsample=4, grid=128),
 }
@@ -313,6 +314,23 @@ def run_render(args, wl, rank, world, local, real_stdout):
         ms_drop = timed(rb.step_resident, drop_steps, 1)
         rb.dropin = False
         rb.rend.cfg.return_samples = False
+    # ---- eval-mode forward (no gradients, no per-sample outputs): sampler + march only -------------------------------
+    ms_eval, eval_steps = float("nan"), min(args.steps, 3)
+    if not args.profile and args.workload != "config4":
+        rb.rend.eval()
+
+        def eval_fwd():       # the reference's eval path takes ONE space cache and its views per call (REN:150-185)
+            V_ = rb.wl["V"]
+            outs = []
+            with torch.no_grad():
+                for p_ in range(rb.wl["P"]):
+                    sl = slice(p_ * V_, (p_ + 1) * V_)
+                    outs.append(rb.rend(rb.rays_d[0][sl], rb.rays_d[1][sl], None, rb.bg, space_cache=rb.sc_d.detach()[p_:p_ + 1],
+                                        text_embed=rb.text_embed[p_:p_ + 1], camera_distances=rb.rays_d[3][sl],
+                                        c2w=rb.rays_d[2][sl])["comp_rgb"])
+            return outs
+        ms_eval = timed(eval_fwd, eval_steps, 1)
+        rb.rend.train()
     h2d, d2h = rb.h2d_bytes(), rb.d2h_bytes()
     del rb
     ops.clear_caches()
@@ -328,10 +346,10 @@ def run_render(args, wl, rank, world, local, real_stdout):
         ops.clear_caches()
         torch.cuda.empty_cache()
 
-    times = torch.tensor([ms_total, ms_e2e, ms_drop, ms_sec], device=dev)
+    times = torch.tensor([ms_total, ms_e2e, ms_drop, ms_sec, ms_eval], device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_drop, ms_sec = times.tolist()
+    ms_total, ms_e2e, ms_drop, ms_sec, ms_eval = times.tolist()
     if rank != 0:
         return
 
@@ -402,6 +420,10 @@ def run_render(args, wl, rank, world, local, real_stdout):
                           "ms_per_step": ms_drop / drop_steps, "steps": drop_steps,
                           "what": "same step with return_samples=True (every per-sample output of the reference renderer "
                                   "materialised, colour decoder at every sample) and the eikonal loss from out['sdf_grad']"}
+    if ms_eval == ms_eval:
+        line["eval_forward"] = {"value": n_rays * world * eval_steps / (ms_eval * 1e-3), "unit": "rays/s",
+                                "ms_per_step": ms_eval / eval_steps, "steps": eval_steps,
+                                "what": "no-grad eval render (importance sampler + march, no per-sample outputs, no masks)"}
     if ms_sec == ms_sec:
         line["secondary"] = {"workload": "config2", **WORKLOADS["config2"], "value": sec_rays * world * sec_steps / (ms_sec * 1e-3),
                              "unit": "rays/s", "ms_per_step": ms_sec / sec_steps, "steps": sec_steps, "warmup": 3}

@@ -101,6 +101,12 @@ int tt_repack_planes(const float* src, int P, int Csrc, int c_off_geo, int c_off
                      float* dst, void* stream);
 /* Adjoint: channel-last rotated gradient -> NCHW [P][6][C][R][R] (overwrites dst). */
 int tt_repack_planes_bwd(const float* gplanes, int P, int C, int R, float* gsrc, void* stream);
+/* Adjoint of the repack WITH the channel split folded in: the VAE decoder's raw output [P][6][Cdst][R][R] (Cdst = 2C,
+ * custom/triplaneturbo/extern/few_step_triplane_dual_sd_modules.py:1012-1020) is the tensor that receives the gradient;
+ * geometry planes write channels [c_off_geo, c_off_geo+C), texture planes [c_off_tex, c_off_tex+C); the other channels
+ * are left untouched (the caller zero-fills, like the gradient of the reference's masked gather). */
+int tt_repack_planes_bwd_split(const float* gplanes, int P, int Cdst, int c_off_geo, int c_off_tex, int C, int R,
+                               float* gsrc, void* stream);
 
 /* ---- geometry on point lists -----------------------------------------------------------
  * Replaces: forward / forward_sdf / forward_field / export of the geometry plugin

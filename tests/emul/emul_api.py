@@ -84,6 +84,12 @@ class Emul:
         self.ok(self.L.tt_repack_planes_bwd(ptr(g), P, C_, R, ptr(out), None), "repack_bwd")
         return out
 
+    def repack_bwd_split(self, g, Cdst, off_geo, off_tex):
+        P, _, R, _, C_ = g.shape
+        out = np.zeros((P, 6, Cdst, R, R), np.float32)
+        self.ok(self.L.tt_repack_planes_bwd_split(ptr(g), P, Cdst, off_geo, off_tex, C_, R, ptr(out), None), "repack_bwd_split")
+        return out
+
     def geometry_fwd(self, planes, wp, cfg, points=None, grid_res=0, normal=True, features=True, deform=False):
         M = points.shape[1] if points is not None else grid_res ** 3
         N = cfg.P * M
@@ -177,6 +183,24 @@ class Emul:
                                      *[ptr(x) for x in opt], rgb_scale, ptr(scratch),
                                      ptr(gplanes), ptr(gw), ptr(gis), None), "render_bwd")
         return gplanes, self.split_wgrad(gw, cfg.C), float(gis[0])
+
+    # ---- stand-alone compositor
+    def composite_fwd(self, alphas, values):
+        a = f32(alphas); n, S = a.shape
+        D = 0 if values is None else values.shape[-1]
+        v = None if values is None else f32(values)
+        w, T, out = np.zeros_like(a), np.zeros_like(a), np.zeros((n, max(D, 1)), np.float32)
+        self.ok(self.L.tt_composite_fwd(ptr(a), ptr(v), n, S, D, ptr(w), ptr(T), ptr(out), None), "composite_fwd")
+        return w, T, out
+
+    def composite_bwd(self, alphas, values, trans, g_out, g_weights):
+        a = f32(alphas); n, S = a.shape
+        D = 0 if values is None else values.shape[-1]
+        v = None if values is None else f32(values)
+        ga = np.zeros_like(a); gv = None if values is None else np.zeros_like(v)
+        go = None if g_out is None else f32(g_out); gw = None if g_weights is None else f32(g_weights)
+        self.ok(self.L.tt_composite_bwd(ptr(a), ptr(v), ptr(f32(trans)), ptr(go), ptr(gw), n, S, D, ptr(ga), ptr(gv), None), "composite_bwd")
+        return ga, gv
 
     # ---- stand-alone plane sampler (tt_sampler.cuh) ------------------------------------------------------------
     def to_channel_last(self, x):

@@ -229,6 +229,36 @@ def test_interpolate_encodings_matches_reference():
     assert max_abs(sdf_direct.reshape(-1), fx["out_sdf_orig"].reshape(-1)) < TOL
 
 
+def test_unsplit_space_cache_is_accepted():
+    """the VAE decoder's raw [P,6,2C,R,R] output rendered directly (channel split folded into the repack) is
+    bit-identical to `decode` + render, forward and gradient (zeros in the unused channel halves)."""
+    fx = load_golden("render_train_c8", DEV)
+    P, V, H, W, ns, nimp = [int(v) for v in fx["meta"][:6]]
+    geom, rend = build_plugins(fx, DEV, ns, nimp)
+    rend.train()
+    sc = fx["space_cache"]
+    C_ = sc.shape[2]
+    g = torch.Generator(device=DEV).manual_seed(3)
+    raw = torch.randn(P, 6, 2 * C_, sc.shape[3], sc.shape[4], device=DEV, generator=g)
+    raw[:, 0:3, :C_] = sc[:, 0:3]
+    raw[:, 3:6, C_:] = sc[:, 3:6]
+    assert torch.equal(geom.decode(raw), sc)                       # the reference's split (few_step…:186-196)
+    kw = dict(rays_o=fx["rays_o"], rays_d=fx["rays_d"], light_positions=None, bg_color=torch.ones(3, device=DEV),
+              text_embed=torch.zeros(P, 4, device=DEV), camera_distances=fx["camera_distances"], c2w=fx["c2w"],
+              t_starts=fx["t_starts"], t_ends=fx["t_ends"])
+    a = sc.clone().requires_grad_(True)
+    b = raw.clone().requires_grad_(True)
+    oa, ob = rend(space_cache=a, **kw), rend(space_cache=b, **kw)
+    for k in ("comp_rgb", "opacity", "depth", "sdf", "sdf_grad", "features", "weights"):
+        assert torch.equal(oa[k], ob[k]), k
+    ga, = torch.autograd.grad(oa["comp_rgb"].square().sum() + oa["opacity"].sum(), a)
+    gb, = torch.autograd.grad(ob["comp_rgb"].square().sum() + ob["opacity"].sum(), b)
+    assert rel_err(gb[:, 0:3, :C_], ga[:, 0:3]) < 1e-5 and rel_err(gb[:, 3:6, C_:], ga[:, 3:6]) < 1e-5
+    assert float(gb[:, 0:3, C_:].abs().max()) == 0.0 and float(gb[:, 3:6, :C_].abs().max()) == 0.0
+    geom.cfg.fuse_channel_split = True
+    assert geom.decode(raw) is raw
+
+
 def test_estimator_accepts_closures():
     """ImportanceEstimator.sampling with a plain callable (the reference's signature, estimators.py:22-101) takes the
     general route and lands on the same intervals as the fused route driven by the renderer's ProposalSpec."""

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtriplane_b200.so")
+# TT_B200_LIB selects another build of the same library (e.g. the -DTT_MEMLOCK=0 build the sanitizer runs compare)
+LIB_PATH = os.environ.get("TT_B200_LIB") or os.path.join(_HERE, "lib", "libtriplane_b200.so")
 
 TT_OK = 0
 fp = C.c_void_p      # device pointers travel as integers
@@ -41,6 +42,7 @@ SIGNATURES = {
     "tt_pack_weights": (C.c_int, [fp] * 9 + [C.c_int, fp, fp]),
     "tt_repack_planes": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp]),
     "tt_repack_planes_bwd": (C.c_int, [fp, C.c_int, C.c_int, C.c_int, fp, fp]),
+    "tt_repack_planes_bwd_split": (C.c_int, [fp] + [C.c_int] * 6 + [fp, fp]),
     "tt_geometry_fwd": (C.c_int, [fp, fp, _cfgp, fp, i64, C.c_int] + [fp] * 6 + [fp]),
     "tt_geometry_bwd_scratch_floats": (C.c_size_t, [_cfgp, i64]),
     "tt_geometry_bwd": (C.c_int, [fp, fp, _cfgp, fp, i64] + [fp] * 4 + [fp, fp, fp, fp]),

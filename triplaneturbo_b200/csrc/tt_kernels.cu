@@ -207,7 +207,7 @@ __global__ void k_repack(const float* __restrict__ src, float* __restrict__ dst,
         }
         __syncthreads();
         for (int c = ty; c < C; c += 8)
-            if (sw0 + tx < R) dst[nchw_plane + ((size_t)c * R + sh) * R + sw0 + tx] = tile[c * 33 + tx];
+            if (sw0 + tx < R) dst[nchw_plane + ((size_t)(coff + c) * R + sh) * R + sw0 + tx] = tile[c * 33 + tx];
     }
 }
 
@@ -884,6 +884,16 @@ int tt_repack_planes_bwd(const float* gplanes, int P, int C, int R, float* gsrc,
     return check_launch("tt_repack_planes_bwd");
 }
 
+int tt_repack_planes_bwd_split(const float* gplanes, int P, int Cdst, int off_geo, int off_tex, int C, int R, float* gsrc,
+                               void* stream) {
+    if (!gplanes || !gsrc) return fail(TT_E_ARG, "tt_repack_planes_bwd_split: NULL pointer%s", "");
+    if (P < 1 || R < 1 || C < 1 || C > 256 || off_geo < 0 || off_tex < 0 || off_geo + C > Cdst || off_tex + C > Cdst)
+        return fail(TT_E_ARG, "tt_repack_planes_bwd_split: bad shape%s", "");
+    dim3 grid((R + 31) / 32, R, P * 6), block(32, 8);
+    TT_LAUNCH(k_repack<true>, grid, block, (size_t)C * 33 * 4, (cudaStream_t)stream, gplanes, gsrc, Cdst, off_geo, off_tex, C, R);
+    return check_launch("tt_repack_planes_bwd_split");
+}
+
 int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cfg, const float* points, int64_t M,
                     int grid_res, float* sdf, float* sdf_orig, float* features, float* normal, float* sdf_grad,
                     float* deformation, void* stream) {
@@ -1235,6 +1245,12 @@ int tt_composite_fwd(const float* alphas, const float* values, int64_t n_rays, i
                      float* trans, float* out, void* stream) {
     if (!alphas || S < 1 || D < 0 || D > 8 || (D > 0 && !values)) return fail(TT_E_ARG, "tt_composite_fwd: bad arguments%s", "");
     if (n_rays <= 0) return TT_OK;
+    if (g_impl >= 1) {      // one warp per ray (coalesced streams); the thread-per-ray kernel stays as the SIMT cross-check
+        const unsigned grid = (unsigned)((n_rays + RAY_WARPS - 1) / RAY_WARPS);
+        if (D <= 4) TT_LAUNCH(k_composite_fwd_w<4>, grid, RAY_WARPS * 32, 0, (cudaStream_t)stream, alphas, values, n_rays, S, D, weights, trans, out);
+        else TT_LAUNCH(k_composite_fwd_w<8>, grid, RAY_WARPS * 32, 0, (cudaStream_t)stream, alphas, values, n_rays, S, D, weights, trans, out);
+        return check_launch("tt_composite_fwd");
+    }
     TT_LAUNCH(k_composite_fwd, (unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream, alphas, values, n_rays, S, D, weights, trans, out);
     return check_launch("tt_composite_fwd");
 }
@@ -1244,6 +1260,12 @@ int tt_composite_bwd(const float* alphas, const float* values, const float* tran
     if (!alphas || !trans || !g_alphas || S < 1 || D < 0 || D > 8 || (D > 0 && !values))
         return fail(TT_E_ARG, "tt_composite_bwd: bad arguments%s", "");
     if (n_rays <= 0) return TT_OK;
+    if (g_impl >= 1) {
+        const unsigned grid = (unsigned)((n_rays + RAY_WARPS - 1) / RAY_WARPS);
+        if (D <= 4) TT_LAUNCH(k_composite_bwd_w<4>, grid, RAY_WARPS * 32, 0, (cudaStream_t)stream, alphas, values, trans, g_out, g_weights, n_rays, S, D, g_alphas, g_values);
+        else TT_LAUNCH(k_composite_bwd_w<8>, grid, RAY_WARPS * 32, 0, (cudaStream_t)stream, alphas, values, trans, g_out, g_weights, n_rays, S, D, g_alphas, g_values);
+        return check_launch("tt_composite_bwd");
+    }
     TT_LAUNCH(k_composite_bwd, (unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream, alphas, values, trans, g_out, g_weights,
         n_rays, S, D, g_alphas, g_values);
     return check_launch("tt_composite_bwd");

@@ -76,6 +76,11 @@ class StableDiffusionTriplaneDualAttention(BaseModule):
         split_channels: Optional[str] = None
         geo_interpolate: str = "v1"
         tex_interpolate: str = "v1"
+        # hand the VAE decoder's raw output [B,6,2C,H,W] to the renderer untouched; the channel split of
+        # `decode` (few_step…diffusion.py:186-196: a boolean-mask gather, 100 MB read + 50 MB written per prompt) then
+        # happens inside the one repack pass (tt_repack_planes with c_off_tex = C).  Off by default: `decode` then returns
+        # the reference's [B,6,C,H,W] tensor.
+        fuse_channel_split: bool = False
 
     cfg: Config
 
@@ -128,8 +133,8 @@ class StableDiffusionTriplaneDualAttention(BaseModule):
     def decode(self, latents: Tensor) -> Tensor:
         """few_step…diffusion.py:180-196.  With a generator attached: VAE decode then channel split."""
         triplane = self.space_generator.forward_decode(latents) if self.space_generator is not None else latents
-        if self.cfg.split_channels is None:
-            return triplane
+        if self.cfg.split_channels is None or self.cfg.fuse_channel_split:
+            return triplane         # un-split: every consumer of the space cache in this package accepts [B,6,2C,H,W]
         B, _, C2, H, W = triplane.shape
         C_ = C2 // 2
         return torch.cat([triplane[:, 0:3, :C_], triplane[:, 3:6, C_:]], dim=1).contiguous()
@@ -158,9 +163,9 @@ class StableDiffusionTriplaneDualAttention(BaseModule):
         B = points.shape[0]
         sc = self._check_cache(space_cache, B)
         if sc.requires_grad and torch.is_grad_enabled():
-            planes = ops.RepackFunction.apply(sc, sc.shape[2], 0, 0)
+            planes = ops.RepackFunction.apply(sc, self.plane_channels, *ops.split_offsets(sc.shape[2], self.plane_channels))
         else:
-            planes = ops.cached_planes(sc)
+            planes = ops.cached_planes(sc, self.plane_channels)
         _, _, R, _, C_ = planes.shape
         grid = sampler.project_onto_planes(sampler.PLANES, points.reshape(B, -1, 3)).float().contiguous()   # [3B,N,2]
         geo = sampler.sample_planes(planes[:, 0:3].reshape(B * 3, R, R, C_), grid, 3, False)
@@ -201,7 +206,7 @@ class StableDiffusionTriplaneDualAttention(BaseModule):
     def forward_field_grid(self, resolution: int, space_cache: Tensor) -> Tuple[Tensor, Optional[Tensor]]:
         """Same as ``forward_field`` on the isosurface helper's vertex grid (threestudio/models/isosurface.py:37-51)
         without materialising the points: the kernel generates vertex (ix*res+iy)*res+iz in place."""
-        planes = ops.cached_planes(space_cache)
+        planes = ops.cached_planes(space_cache, self.plane_channels)
         wpack = ops.cached_wpack(self.sdf_network.weights(), self.feature_network.weights(),
                                  self._deformation_weights(), self.plane_channels)
         want = ["sdf"] + (["deformation"] if self.cfg.isosurface_deformable_grid else [])
@@ -222,7 +227,7 @@ class StableDiffusionTriplaneDualAttention(BaseModule):
             return sdf, None
         if need_grad:       # mesh renderer: gradients reach the planes, the SDF decoder and the deformation decoder
             return ops.FieldFunction.apply(sc, *self.decoder_weights(), *dw, pts, self.path_scalars())
-        planes = ops.cached_planes(sc)
+        planes = ops.cached_planes(sc, self.plane_channels)
         wpack = ops.cached_wpack(self.sdf_network.weights(), self.feature_network.weights(),
                                  self._deformation_weights(), self.plane_channels)
         want = ["sdf"] + (["deformation"] if with_deformation else [])
@@ -236,7 +241,7 @@ class StableDiffusionTriplaneDualAttention(BaseModule):
         """few_step…diffusion.py:402-430: features at surface points (vertex colours)."""
         orig = points.shape
         sc = self._check_cache(space_cache, 1)
-        planes = ops.cached_planes(sc)
+        planes = ops.cached_planes(sc, self.plane_channels)
         wpack = ops.cached_wpack(self.sdf_network.weights(), self.feature_network.weights(),
                                  self._deformation_weights(), self.plane_channels)
         out = ops.geometry_fwd(planes, wpack, self.path_scalars(), points.detach().reshape(1, -1, 3), 0, ["features"])

@@ -103,14 +103,34 @@ def repack_planes(space_cache: Tensor, C_: Optional[int] = None, off_geo: int = 
     return out
 
 
-def repack_planes_bwd(gplanes: Tensor) -> Tensor:
+def repack_planes_bwd(gplanes: Tensor, Csrc: Optional[int] = None) -> Tensor:
+    """Channel-last rotated gradient [P,6,R,R,C] -> gradient of the NCHW space cache [P,6,Csrc,R,R].  Csrc == 2C: the cache
+    was the VAE decoder's raw output and the channel split was folded into the repack (geometry planes own channels [0,C),
+    texture planes [C,2C)); the unused halves are zero like the gradient of the reference's masked gather."""
     g = _need(gplanes, "gplanes")
     P, _, R, _, C_ = g.shape
-    out = torch.empty((P, 6, C_, R, R), device=g.device, dtype=torch.float32)
+    Csrc = Csrc or C_
     L = _lib()
     with torch.cuda.device(g.device):
-        _cabi.check(L, L.tt_repack_planes_bwd(_ptr(g), P, C_, R, _ptr(out), _stream(g.device)), "tt_repack_planes_bwd")
+        if Csrc == C_:
+            out = torch.empty((P, 6, C_, R, R), device=g.device, dtype=torch.float32)
+            _cabi.check(L, L.tt_repack_planes_bwd(_ptr(g), P, C_, R, _ptr(out), _stream(g.device)), "tt_repack_planes_bwd")
+        else:
+            off_geo, off_tex = split_offsets(Csrc, C_)
+            out = torch.zeros((P, 6, Csrc, R, R), device=g.device, dtype=torch.float32)
+            _cabi.check(L, L.tt_repack_planes_bwd_split(_ptr(g), P, Csrc, off_geo, off_tex, C_, R, _ptr(out), _stream(g.device)),
+                        "tt_repack_planes_bwd_split")
     return out
+
+
+def split_offsets(Csrc: int, C_: int) -> Tuple[int, int]:
+    """Channel offsets of the geometry / texture planes inside a space cache with Csrc channels (split_channels v1,
+    few_step…diffusion.py:186-196: geometry = first half of planes 0-2, texture = second half of planes 3-5)."""
+    if Csrc == C_:
+        return 0, 0
+    if Csrc == 2 * C_:
+        return 0, C_
+    raise _cabi.TTError(f"space cache has {Csrc} channels; the decoders expect {C_} (or the un-split {2 * C_})")
 
 
 def pack_weights(sdf: Sequence[Tensor], feature: Optional[Sequence[Tensor]], deformation: Optional[Sequence[Tensor]],
@@ -338,8 +358,13 @@ _weights_caches = {}      # one slot per weight-set shape (with / without the de
                           # the renderer (6 tensors) and the field query (9 tensors) alternate inside a step
 
 
-def cached_planes(space_cache: Tensor) -> Tensor:
-    return _planes_cache.get([space_cache], lambda: repack_planes(space_cache.detach()))
+def cached_planes(space_cache: Tensor, C_: Optional[int] = None) -> Tensor:
+    """Repacked planes of a space cache [P,6,C,R,R] -- or of the VAE decoder's raw output [P,6,2C,R,R] (pass C_): the
+    channel split of ``decode`` then happens inside the one repack pass instead of a masked gather + copy."""
+    Csrc = space_cache.shape[2]
+    C_ = C_ or Csrc
+    off_geo, off_tex = split_offsets(Csrc, C_)
+    return _planes_cache.get([space_cache], lambda: repack_planes(space_cache.detach(), C_, off_geo, off_tex))
 
 
 def cached_wpack(sdf_w, feat_w, def_w, C_) -> Tensor:
@@ -383,8 +408,9 @@ class RenderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, space_cache, ws0, ws1, ws2, wf0, wf1, wf2, inv_std, rays_o, rays_d, t_starts, t_ends,
                 scalars: PathScalars, rays_per_cache: int, rgb_grad_scale: float, extras: bool):
-        C_ = space_cache.shape[2]
-        planes = cached_planes(space_cache)
+        C_ = ws0.shape[1]                   # plane channels = input width of the SDF decoder
+        ctx.Csrc = space_cache.shape[2]     # == C_, or 2 C_ for an un-split cache (channel split folded into the repack)
+        planes = cached_planes(space_cache, C_)
         wpack = cached_wpack([ws0, ws1, ws2], [wf0, wf1, wf2], None, C_)
         need_grad = any(ctx.needs_input_grad[:8])
         out = render_fwd(planes, wpack, scalars, rays_o, rays_d, rays_per_cache, t_starts, t_ends, need_grad, extras)
@@ -417,7 +443,7 @@ class RenderFunction(torch.autograd.Function):
                                           g_acc, None if g_sdf is None else g_sdf.reshape(-1), g_sdf_grad, g_normal,
                                           g_features, None if g_weights is None else g_weights.reshape(-1),
                                           ctx.rgb_grad_scale, need_planes, need_w, ctx.needs_input_grad[7])
-        g_sc = repack_planes_bwd(gplanes) if need_planes else None
+        g_sc = repack_planes_bwd(gplanes, ctx.Csrc) if need_planes else None
         gws = split_wgrad(gw, ctx.C) if need_w else [None] * 6
         gws = [g if ctx.needs_input_grad[1 + i] else None for i, g in enumerate(gws)]
         g_inv = gis.reshape(()) if gis is not None else None
@@ -432,8 +458,9 @@ class GeometryFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, space_cache, ws0, ws1, ws2, wf0, wf1, wf2, points, scalars: PathScalars, output_normal: bool):
-        C_ = space_cache.shape[2]
-        planes = cached_planes(space_cache)
+        C_ = ws0.shape[1]
+        ctx.Csrc = space_cache.shape[2]
+        planes = cached_planes(space_cache, C_)
         wpack = cached_wpack([ws0, ws1, ws2], [wf0, wf1, wf2], None, C_)
         want = ["sdf", "sdf_orig", "features"] + (["normal", "sdf_grad"] if output_normal else [])
         out = geometry_fwd(planes, wpack, scalars, points, 0, want)
@@ -458,7 +485,7 @@ class GeometryFunction(torch.autograd.Function):
         with _impl_scope(ctx.impl):
             gplanes, gw = geometry_bwd(planes, wpack, ctx.scalars, points, g, g_features, g_normal, g_sdf_grad,
                                        need_planes, need_w)
-        g_sc = repack_planes_bwd(gplanes) if need_planes else None
+        g_sc = repack_planes_bwd(gplanes, ctx.Csrc) if need_planes else None
         gws = split_wgrad(gw, ctx.C) if need_w else [None] * 6
         gws = [x if ctx.needs_input_grad[1 + i] else None for i, x in enumerate(gws)]
         return (g_sc, *gws, None, None, None)
@@ -492,8 +519,9 @@ class FieldFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, space_cache, ws0, ws1, ws2, wf0, wf1, wf2, wd0, wd1, wd2, points, scalars: PathScalars):
-        C_ = space_cache.shape[2]
-        planes = cached_planes(space_cache)
+        C_ = ws0.shape[1]
+        ctx.Csrc = space_cache.shape[2]
+        planes = cached_planes(space_cache, C_)
         wpack = cached_wpack([ws0, ws1, ws2], [wf0, wf1, wf2], [wd0, wd1, wd2], C_)
         out = geometry_fwd(planes, wpack, scalars, points, 0, ["sdf", "deformation"])
         ctx.scalars, ctx.C, ctx.impl = scalars, C_, get_impl()
@@ -510,7 +538,7 @@ class FieldFunction(torch.autograd.Function):
             gplanes, gw, gwd = field_bwd(planes, wpack, ctx.scalars, points,
                                          None if g_sdf is None else g_sdf.reshape(-1), g_def, need_planes, need_w,
                                          need_wd)
-        g_sc = repack_planes_bwd(gplanes) if need_planes else None
+        g_sc = repack_planes_bwd(gplanes, ctx.Csrc) if need_planes else None
         gws = split_wgrad(gw, ctx.C)[:3] if need_w else [None] * 3
         gws = [x if ctx.needs_input_grad[1 + i] else None for i, x in enumerate(gws)]
         if need_wd:
@@ -534,15 +562,7 @@ class RepackFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        P, _, Csrc, R, _ = ctx.shape
-        g_nchw = repack_planes_bwd(g.contiguous())                       # [P,6,C,R,R]
-        C_ = g_nchw.shape[2]
-        if Csrc == C_:
-            return g_nchw, None, None, None
-        full = torch.zeros(ctx.shape, device=g.device, dtype=torch.float32)
-        full[:, 0:3, ctx.off[0]:ctx.off[0] + C_] = g_nchw[:, 0:3]
-        full[:, 3:6, ctx.off[1]:ctx.off[1] + C_] = g_nchw[:, 3:6]
-        return full, None, None, None
+        return repack_planes_bwd(g.contiguous(), ctx.shape[2]), None, None, None
 
 
 class CompositeFunction(torch.autograd.Function):

@@ -266,11 +266,11 @@ class GenerativeSpaceSDFVolumeRenderer(BaseModule):
         geom = self.geometry
         scalars = self.path_scalars()
         weights = geom.decoder_weights()
-        C_ = space_cache.shape[2]
+        C_ = geom.plane_channels
 
         if t_starts is None:       # REN:243-316
             spec = ImportanceEstimator.ProposalSpec(
-                ops.cached_planes(space_cache),
+                ops.cached_planes(space_cache, C_),
                 ops.cached_wpack(weights[:3], weights[3:], geom._deformation_weights(), C_), scalars, o, d,
                 rays_per_cache)
             t_starts, t_ends = self.estimator.sampling(
