@@ -1097,9 +1097,14 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
                     const int64_t ctas_t = (tiles + GT - 1) / GT;
                     const unsigned grid_t = (unsigned)(ctas_t < (int64_t)num_sms() ? ctas_t : num_sms());
                     if (cudaMemsetAsync(hid, 0, hid_floats(cfg) * sizeof(float), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
-                    if (int e = set_smem(k_bwd_tex_tc<kC>, smt)) return e;
                     ts.index = tex_list; ts.count = tex_count;
-                    TT_LAUNCH(k_bwd_tex_tc<kC>, grid_t, GT * TC_GROUP, smt, st, planes, wpack, *cfg, ts, N, gf, tex_masks, hid, gw);
+                    if (!src.points && src.rs.S >= 256) {      // long rays: consecutive samples share texel cells
+                        if (int e = set_smem((k_bwd_tex_tc<kC, true>), smt)) return e;
+                        TT_LAUNCH((k_bwd_tex_tc<kC, true>), grid_t, GT * TC_GROUP, smt, st, planes, wpack, *cfg, ts, N, gf, tex_masks, hid, gw);
+                    } else {
+                        if (int e = set_smem((k_bwd_tex_tc<kC, false>), smt)) return e;
+                        TT_LAUNCH((k_bwd_tex_tc<kC, false>), grid_t, GT * TC_GROUP, smt, st, planes, wpack, *cfg, ts, N, gf, tex_masks, hid, gw);
+                    }
                     if (int e = check_launch("k_bwd_tex_tc")) return e;
                     if (gplanes) {
                         const size_t smh = (size_t)64 * kC * 4;

@@ -334,7 +334,9 @@ struct BwdTexSmem {
     static_assert(128 * (C + 4) <= wg_tile_floats(64) && 128 * HS <= wg_tile_floats(64), "stage must fit in the B tile");
 };
 
-template <int C>
+// RL: run-length merged scatter of the hidden gradient (wins when many consecutive samples of a ray share texel cells:
+// config 2, 289 samples per ray: 109 vs 113 ms) or the plain one (config 3, 193 samples per ray at 512^2: 432 vs 460 ms).
+template <int C, bool RL>
 __global__ void __launch_bounds__(BwdTexSmem<C>::G * TC_GROUP, 1)
 k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_config cfg, TcSrc src, int64_t N,
              const float* __restrict__ gf_i, const uint64_t* __restrict__ masks, float* __restrict__ hid,
@@ -508,7 +510,22 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
                 *reinterpret_cast<float4*>(tap_w + tg * 4) = w4;
             }
             group_sync(group);
-            coop_scatter_rl<16, 1>(hid + (size_t)k * hs, 3 * hs, 0, 64, tap_o, tap_w, pbase, stage, HS, tg);
+            if (RL) coop_scatter_rl<16, 1>(hid + (size_t)k * hs, 3 * hs, 0, 64, tap_o, tap_w, pbase, stage, HS, tg);
+            else {   // plain scatter of the 64-wide hidden gradient: item = (point, 16-byte chunk), 4 vector reductions each
+#pragma unroll 4
+                for (int j = 0; j < 16; ++j) {
+                    const int item = tg + TC_GROUP * j;
+                    const int pt = item >> 4, ch = item & 15;
+                    const float4 v = *reinterpret_cast<const float4*>(stage + pt * HS + ch * 4);
+                    const int4 o4 = *reinterpret_cast<const int4*>(tap_o + pt * 4);
+                    const float4 w4 = *reinterpret_cast<const float4*>(tap_w + pt * 4);
+                    float* pb = hid + (size_t)pbase[pt] * 3 * hs + (size_t)k * hs + ch * 4;
+                    if (w4.x != 0.f) red_add4(pb + (size_t)o4.x * 64, make_float4(v.x * w4.x, v.y * w4.x, v.z * w4.x, v.w * w4.x));
+                    if (w4.y != 0.f) red_add4(pb + (size_t)o4.y * 64, make_float4(v.x * w4.y, v.y * w4.y, v.z * w4.y, v.w * w4.y));
+                    if (w4.z != 0.f) red_add4(pb + (size_t)o4.z * 64, make_float4(v.x * w4.z, v.y * w4.z, v.z * w4.z, v.w * w4.z));
+                    if (w4.w != 0.f) red_add4(pb + (size_t)o4.w * 64, make_float4(v.x * w4.w, v.y * w4.w, v.z * w4.w, v.w * w4.w));
+                }
+            }
             group_sync(group);
         }
         any_tile = true;
