@@ -65,6 +65,8 @@ typedef struct {
     float render_step_size;  /* neus_volume_renderer.py:84-86 */
     int32_t flags;           /* TT_FLAG_* */
 } tt_config;
+#define TT_FLAG_PRECISE_BWD 2  /* tt_render_bwd / tt_geometry_bwd: run the colour decoder's backward layers as 3xTF32 (fp32-equivalent)
+                                  instead of single-pass TF32; one 128-thread group per CTA fits then (slower) */
 #define TT_FLAG_ALL_FEATURES 1 /* tt_render_fwd: evaluate the colour decoder at every sample, not only where the
                                   transmittance is > 0 (needed when `features` is returned to the caller) */
 

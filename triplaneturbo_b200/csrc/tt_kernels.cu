@@ -143,6 +143,19 @@ static int launch_tex_decoder(const float* planes, const float* wpack, const tt_
     return check_launch("k_tex_tc");
 }
 
+// colour backward: RL = run-length merged hidden-gradient scatter, P3 = 3xTF32 layers (TT_FLAG_PRECISE_BWD)
+template <int kC, bool RL, bool P3>
+static int launch_bwd_tex(const float* planes, const float* wpack, const tt_config* cfg, const TcSrc& ts, int64_t N, int64_t tiles,
+                          const float* gf, const uint64_t* tex_masks, float* hid, float* gw, cudaStream_t st) {
+    constexpr int GT = BwdTexSmem<kC, P3>::G;
+    const size_t smx = (size_t)BwdTexSmem<kC, P3>::TOTAL * 4;
+    const int64_t ctas_t = (tiles + GT - 1) / GT;
+    const unsigned grid_t = (unsigned)(ctas_t < (int64_t)num_sms() ? ctas_t : num_sms());
+    if (int e = set_smem((k_bwd_tex_tc<kC, RL, P3>), smx)) return e;
+    TT_LAUNCH((k_bwd_tex_tc<kC, RL, P3>), grid_t, GT * TC_GROUP, smx, st, planes, wpack, *cfg, ts, N, gf, tex_masks, hid, gw);
+    return check_launch("k_bwd_tex_tc");
+}
+
 static inline size_t slab_bytes(int rows) { return (size_t)rows * ST * sizeof(float); }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 
@@ -1093,19 +1106,14 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
                     TT_LAUNCH(k_bwd_geo_tc<kC>, grid_g, GG * TC_GROUP, smg, st, planes, wpack, *cfg, ts, N, gs, u, tex_masks, gplanes, gw);
                     if (int e = check_launch("k_bwd_geo_tc")) return e;
                     // colour branch: per-sample kernel scatters the 64-wide hidden gradient, then two dense products
-                    constexpr int GT = BwdTexSmem<kC>::G;
-                    const int64_t ctas_t = (tiles + GT - 1) / GT;
-                    const unsigned grid_t = (unsigned)(ctas_t < (int64_t)num_sms() ? ctas_t : num_sms());
                     if (cudaMemsetAsync(hid, 0, hid_floats(cfg) * sizeof(float), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
                     ts.index = tex_list; ts.count = tex_count;
-                    if (!src.points && src.rs.S >= 256) {      // long rays: consecutive samples share texel cells
-                        if (int e = set_smem((k_bwd_tex_tc<kC, true>), smt)) return e;
-                        TT_LAUNCH((k_bwd_tex_tc<kC, true>), grid_t, GT * TC_GROUP, smt, st, planes, wpack, *cfg, ts, N, gf, tex_masks, hid, gw);
-                    } else {
-                        if (int e = set_smem((k_bwd_tex_tc<kC, false>), smt)) return e;
-                        TT_LAUNCH((k_bwd_tex_tc<kC, false>), grid_t, GT * TC_GROUP, smt, st, planes, wpack, *cfg, ts, N, gf, tex_masks, hid, gw);
-                    }
-                    if (int e = check_launch("k_bwd_tex_tc")) return e;
+                    const bool rl = !src.points && src.rs.S >= 256;        // long rays: consecutive samples share texel cells
+                    const bool p3 = (cfg->flags & TT_FLAG_PRECISE_BWD) != 0 && (size_t)BwdTexSmem<kC, true>::TOTAL * 4 <= kMaxSmem;
+                    if (p3) { if (int e = rl ? launch_bwd_tex<kC, true, true>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)
+                                                 : launch_bwd_tex<kC, false, true>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)) return e; }
+                    else { if (int e = rl ? launch_bwd_tex<kC, true, false>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)
+                                              : launch_bwd_tex<kC, false, false>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)) return e; }
                     if (gplanes) {
                         const size_t smh = (size_t)64 * kC * 4;
                         const int64_t items = (int64_t)cfg->P * cfg->R * cfg->R * (kC / 4);

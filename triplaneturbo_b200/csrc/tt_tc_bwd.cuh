@@ -319,11 +319,18 @@ k_bwd_geo_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
 // Per tile: gather e_k (3 planes) -> h1 = relu(Σ W1_k e_k) -> z2 = W2 h1 (single-pass TF32, masks from the forward),
 // g2 = m2 ⊙ W3ᵀ gf, dW2 += g2 h1ᵀ (TMEM accumulator), g1 = m1 ⊙ W2ᵀ g2, dW3 += gf h2ᵀ (SIMT from the h2 operand tile),
 // scatter g1·w into H.  G independent 128-thread groups per CTA; TMEM per group: A [0,64) dW2 [64,128) D [128,192).
-template <int C>
+template <int C, bool P3 = false>
 struct BwdTexSmem {
     static constexpr int HS = 68;                                               // row stride of the staged g1 [128][64]
-    static constexpr int W1H = 0, W2H = W1H + 3 * 64 * C, W2TH = W2H + 4096, W3 = W2TH + 4096;
+    // weight tiles as tf32 hi + exact remainder: the recomputed activations and the adjoint layer run as 3xTF32 like the
+    // forward (round 2, DESIGN 4.2: with single-pass layers the colour decoder's weight gradients were 200x less accurate
+    // than an fp32 run; the kernel is bound by its vector reductions, the extra MMAs are free)
+    // P3 (TT_FLAG_PRECISE_BWD): the lo tiles exist and the layers run as 3xTF32; the operand tiles of the weight-gradient
+    // contraction (2 x 36 KB per group) then leave room for ONE group per CTA only: measured 651 vs 432 ms at config 3.
+    static constexpr int W1H = 0, W1L = W1H + 3 * 64 * C, W2H = W1L + (P3 ? 3 * 64 * C : 0), W2L = W2H + 4096;
+    static constexpr int W2TH = W2L + (P3 ? 4096 : 0), W2TL = W2TH + 4096, W3 = W2TL + (P3 ? 4096 : 0);
     static constexpr int GROUP0 = W3 + 192;
+    static constexpr uint32_t COL_ALO = 192;                                    // TMEM: A hi [0,64) dW2 [64,128) D [128,192) A lo [192,256)
     static constexpr int AT = 0, BT = AT + wg_tile_floats(64), STAGE = BT;      // STAGE aliases the B tile
     static constexpr int TAP_O = BT + wg_tile_floats(64), TAP_W = TAP_O + 128 * 4, PBASE = TAP_W + 128 * 4;
     static constexpr int GF = PBASE + 128;
@@ -336,25 +343,34 @@ struct BwdTexSmem {
 
 // RL: run-length merged scatter of the hidden gradient (wins when many consecutive samples of a ray share texel cells:
 // config 2, 289 samples per ray: 109 vs 113 ms) or the plain one (config 3, 193 samples per ray at 512^2: 432 vs 460 ms).
-template <int C, bool RL>
-__global__ void __launch_bounds__(BwdTexSmem<C>::G * TC_GROUP, 1)
+template <int C, bool RL, bool P3>
+__global__ void __launch_bounds__(BwdTexSmem<C, P3>::G * TC_GROUP, 1)
 k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_config cfg, TcSrc src, int64_t N,
              const float* __restrict__ gf_i, const uint64_t* __restrict__ masks, float* __restrict__ hid,
              float* __restrict__ gw) {
     TT_SHARED(smem);
-    using L = BwdTexSmem<C>;
+    using L = BwdTexSmem<C, P3>;
     constexpr int SP = C + 4, HS = L::HS, G = L::G, NT = G * TC_GROUP;
+    constexpr int PASSES = P3 ? 3 : 1;
     const int tid = threadIdx.x, group = tid / TC_GROUP, tg = tid % TC_GROUP, warp = tid >> 5;
     const WOff wo = woff(C);
     const GOff go = goff(C);
-    for (int i = tid; i < 3 * 64 * C; i += NT) {              // W1f as three [64][C] K-major tiles (single pass)
-        const int k = i / (64 * C), r = i - k * 64 * C, n = r / C, kk = r % C;
-        smem[L::W1H + k * 64 * C + btile_off(n, kk, C)] = tf32_rn(__ldg(wp + wo.w1f + n * 3 * C + k * C + kk));
-    }
-    for (int i = tid; i < 4096; i += NT) {
-        const int n = i / 64, k = i % 64;
-        smem[L::W2H + btile_off(n, k, 64)] = tf32_rn(__ldg(wp + wo.w2f + n * 64 + k));
-        smem[L::W2TH + btile_off(n, k, 64)] = tf32_rn(__ldg(wp + wo.w2f + k * 64 + n));
+    if (P3) {
+        for (int k = 0; k < 3; ++k)      // W1f as three [64][C] K-major tiles (one per texture plane), tf32 hi + remainder
+            btile_fill(smem + L::W1H + k * 64 * C, smem + L::W1L + k * 64 * C, 64, C,
+                       [&](int n, int kk) { return __ldg(wp + wo.w1f + n * 3 * C + k * C + kk); }, tid, NT);
+        btile_fill(smem + L::W2H, smem + L::W2L, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2f + n * 64 + k); }, tid, NT);
+        btile_fill(smem + L::W2TH, smem + L::W2TL, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2f + k * 64 + n); }, tid, NT);
+    } else {
+        for (int i = tid; i < 3 * 64 * C; i += NT) {          // single pass: round-to-nearest tf32 weights
+            const int k = i / (64 * C), r = i - k * 64 * C, n = r / C, kk = r % C;
+            smem[L::W1H + k * 64 * C + btile_off(n, kk, C)] = tf32_rn(__ldg(wp + wo.w1f + n * 3 * C + k * C + kk));
+        }
+        for (int i = tid; i < 4096; i += NT) {
+            const int n = i / 64, k = i % 64;
+            smem[L::W2H + btile_off(n, k, 64)] = tf32_rn(__ldg(wp + wo.w2f + n * 64 + k));
+            smem[L::W2TH + btile_off(n, k, 64)] = tf32_rn(__ldg(wp + wo.w2f + k * 64 + n));
+        }
     }
     for (int i = tid; i < 192; i += NT) smem[L::W3 + i] = __ldg(wp + wo.w3f + i);
     float* gsm = smem + L::GROUP0 + group * L::GROUP_FLOATS;
@@ -374,9 +390,9 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
     u.mbar = smem_u32(mbars + group); u.phase = 0; u.group = group;
     const bool leader = tg == 0;
     BTile bW1[3];
-    for (int k = 0; k < 3; ++k) bW1[k] = btile_make(smem + L::W1H + k * 64 * C, smem + L::W1H + k * 64 * C, 64, C);
-    const BTile bW2 = btile_make(smem + L::W2H, smem + L::W2H, 64, 64);
-    const BTile bW2T = btile_make(smem + L::W2TH, smem + L::W2TH, 64, 64);
+    for (int k = 0; k < 3; ++k) bW1[k] = btile_make(smem + L::W1H + k * 64 * C, smem + L::W1L + k * 64 * C, 64, C);
+    const BTile bW2 = btile_make(smem + L::W2H, smem + L::W2L, 64, 64);
+    const BTile bW2T = btile_make(smem + L::W2TH, smem + L::W2TL, 64, 64);
     float* At = gsm + L::AT; float* Bt = gsm + L::BT;
     const uint32_t at_addr = smem_u32(At), bt_addr = smem_u32(Bt);
     int* tap_o = reinterpret_cast<int*>(gsm + L::TAP_O);
@@ -435,9 +451,9 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
                 e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
             }
             if (k > 0) umma_wait(u);          // previous chunk's MMAs are done reading A
-            umma_put_A1<C>(u, e);
+            if (P3) umma_put_A_ex<C>(u, e, TC_COL_AHI, L::COL_ALO); else umma_put_A1<C>(u, e);
             group_sync(group);
-            if (leader) { umma_mma<1>(u, bW1[k], C, k > 0); umma_commit(u); }
+            if (leader) { umma_mma_ex<PASSES>(u, bW1[k], C, k > 0, TC_COL_AHI, L::COL_ALO, TC_COL_D); umma_commit(u); }
         }
         umma_wait(u);
         umma_get_D<64>(u, d);
@@ -451,12 +467,12 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
                 const float v = gf[0] * w3[j] + gf[1] * w3[64 + j] + gf[2] * w3[128 + j];
                 At[wg_off(j, tg)] = ((m2 >> j) & 1ull) ? tf32_rn(v) : 0.f;           // g2 -> A tile of dW2
             }
-            umma_put_A1<64>(u, h);
+            if (P3) umma_put_A_ex<64>(u, h, TC_COL_AHI, L::COL_ALO); else umma_put_A1<64>(u, h);
             async_proxy_fence();
             group_sync(group);
             if (leader) {
                 if (gw) umma_mma_ss(u, at_addr, bt_addr, 64, L::COL_GW2, any_tile);
-                umma_mma<1>(u, bW2, 64, false);
+                umma_mma_ex<PASSES>(u, bW2, 64, false, TC_COL_AHI, L::COL_ALO, TC_COL_D);
                 umma_commit(u);
             }
             umma_wait(u);
@@ -476,7 +492,11 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
                 const float v = gf[0] * w3[j] + gf[1] * w3[64 + j] + gf[2] * w3[128 + j];
                 g2[j] = ((m2 >> j) & 1ull) ? v : 0.f;
             }
-            umma_layer<64, 64, 1>(u, leader, g2, bW2T, g1);      // (its group_sync also publishes the h2 tile)
+            if (P3) umma_put_A_ex<64>(u, g2, TC_COL_AHI, L::COL_ALO); else umma_put_A1<64>(u, g2);
+            group_sync(u.group);                                 // (also publishes the h2 tile)
+            if (leader) { umma_mma_ex<PASSES>(u, bW2T, 64, false, TC_COL_AHI, L::COL_ALO, TC_COL_D); umma_commit(u); }
+            umma_wait(u);
+            umma_get_D<64>(u, g1);
         }
         if (gw) {
 #pragma unroll 4

@@ -336,6 +336,35 @@ __device__ __forceinline__ void umma_get_D(const Umma& u, float (&d)[N], uint32_
     tmem_wait_ld();
     tc_fence_before();
 }
+// this thread's row x[0..K) -> TMEM columns col_hi.. (tf32 hi) and col_lo.. (exact remainder), explicit columns
+template <int K>
+__device__ __forceinline__ void umma_put_A_ex(const Umma& u, const float (&x)[K], uint32_t col_hi, uint32_t col_lo) {
+    constexpr int K32 = K / 32 * 32;
+#pragma unroll
+    for (int k0 = 0; k0 < K32; k0 += 32) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float h = tf32_hi(x[k0 + j]);
+            hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(x[k0 + j] - h);
+        }
+        tmem_st32(u.tmem + u.lane_base + col_hi + k0, hi);
+        tmem_st32(u.tmem + u.lane_base + col_lo + k0, lo);
+    }
+#pragma unroll
+    for (int k0 = K32; k0 < K; k0 += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float h = tf32_hi(x[k0 + j]);
+            hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(x[k0 + j] - h);
+        }
+        tmem_st8(u.tmem + u.lane_base + col_hi + k0, hi);
+        tmem_st8(u.tmem + u.lane_base + col_lo + k0, lo);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+}
 // one full layer: put A, barrier, one thread issues + commits, everybody waits, get D
 template <int K, int N, int PASSES>
 __device__ __forceinline__ void umma_layer(Umma& u, bool leader, const float (&x)[K], const BTile& b, float (&d)[N]) {

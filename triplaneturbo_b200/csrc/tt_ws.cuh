@@ -540,36 +540,6 @@ __device__ __forceinline__ void ws_gather_plane(const float* __restrict__ planes
     }
 }
 
-// this thread's row x[0..K) -> TMEM columns col_hi.. (tf32 hi) and col_lo.. (exact remainder)
-template <int K>
-__device__ __forceinline__ void ws_put_row(const Umma& u, const float (&x)[K], uint32_t col_hi, uint32_t col_lo) {
-    constexpr int K32 = K / 32 * 32;
-#pragma unroll
-    for (int k0 = 0; k0 < K32; k0 += 32) {
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float h = tf32_hi(x[k0 + j]);
-            hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(x[k0 + j] - h);
-        }
-        tmem_st32(u.tmem + u.lane_base + col_hi + k0, hi);
-        tmem_st32(u.tmem + u.lane_base + col_lo + k0, lo);
-    }
-#pragma unroll
-    for (int k0 = K32; k0 < K; k0 += 8) {
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float h = tf32_hi(x[k0 + j]);
-            hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(x[k0 + j] - h);
-        }
-        tmem_st8(u.tmem + u.lane_base + col_hi + k0, hi);
-        tmem_st8(u.tmem + u.lane_base + col_lo + k0, lo);
-    }
-    tmem_wait_st();
-    tc_fence_before();
-}
-
 template <int C>
 __global__ void __launch_bounds__(WS_THREADS, 1) k_tex_ws(const float* __restrict__ planes, const float* __restrict__ wp,
                                                          tt_config cfg, TcSrc src, int64_t N, float* feat_o,
@@ -679,7 +649,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_tex_ws(const float* __restric
                     e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
                 }
                 if (L::NREG == 1 && k > 0) umma_wait(u);          // the previous plane's MMAs are done reading A
-                ws_put_row<C>(u, e, L::col_hi(k), L::col_lo(k));
+                umma_put_A_ex<C>(u, e, L::col_hi(k), L::col_lo(k));
                 mbar_arrive(smem_u32(empty + sb));
                 group_sync(u.group);
                 if (leader) {

@@ -274,6 +274,16 @@ def render_fwd(planes, wpack, s: PathScalars, rays_o, rays_d, rays_per_cache, t_
     return out
 
 
+PRECISE_BACKWARD = False      # TT_FLAG_PRECISE_BWD for every backward of this process (see set_precise_backward)
+
+
+def set_precise_backward(on: bool):
+    """Run the colour decoder's backward layers as 3xTF32 (fp32-equivalent gradients of the feature network)
+    instead of single-pass TF32.  Slower: one group per CTA fits (config 3: 651 vs 432 ms for that kernel)."""
+    global PRECISE_BACKWARD
+    PRECISE_BACKWARD = bool(on)
+
+
 def render_bwd(planes, wpack, s: PathScalars, rays_o, rays_d, rays_per_cache, t_starts, t_ends, saved: dict,
                g_acc, g_sdf=None, g_sdf_grad=None, g_normal=None, g_features=None, g_weights=None,
                rgb_grad_scale: float = 1.0, need_planes=True, need_w=True, need_inv_std=False):
@@ -283,7 +293,7 @@ def render_bwd(planes, wpack, s: PathScalars, rays_o, rays_d, rays_per_cache, t_
     n = o.shape[0]
     t0, t1, stride, S = _intervals(t_starts, t_ends)
     L = _lib()
-    cfg = _cfg(C_, R, P, rays_per_cache, s)
+    cfg = _cfg(C_, R, P, rays_per_cache, s, 2 if PRECISE_BACKWARD else 0)
     scratch = torch.empty(L.tt_render_bwd_scratch_floats(C.byref(cfg), n, S), device=dev, dtype=torch.float32)
     gplanes = torch.zeros_like(planes) if need_planes else None
     gw = torch.zeros(L.tt_wgrad_floats(C_), device=dev, dtype=torch.float32) if need_w else None
