@@ -235,13 +235,39 @@ class RenderBench:
     def step_resident(self):
         return self.step(self.sc_d, *self.rays_d)
 
-    def step_e2e(self):
+    def _upload(self):
+        """H2D of one step's inputs (pinned host buffers) on the copy stream; returns the device tensors + a ready event."""
         dev = self.dev
-        sc = self.sc_h.to(dev, non_blocking=True).requires_grad_(True)
-        ro, rd, c2w_, cd = [t.to(dev, non_blocking=True) for t in self.rays_h]
-        out, loss, grads = self.step(sc, ro, rd, c2w_, cd)
-        img = out["comp_rgb"].detach().to("cpu", non_blocking=True)
-        return img, loss.detach().to("cpu", non_blocking=True)
+        with torch.cuda.stream(self.copy_stream):
+            sc = self.sc_h.to(dev, non_blocking=True)
+            rays = [t.to(dev, non_blocking=True) for t in self.rays_h]
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return sc, rays, ev
+
+    def step_e2e(self):
+        """One step with host buffers: this step's inputs were uploaded on the copy stream while the previous step computed
+        (every step still uploads its own inputs and reads its own result back inside the timed region)."""
+        if not hasattr(self, "copy_stream"):
+            self.copy_stream = torch.cuda.Stream(self.dev)
+            self._next = self._upload()
+        sc, rays, ev = self._next
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(ev)
+        for t in [sc] + rays:
+            t.record_stream(cur)
+        self._next = self._upload()                       # overlaps with this step's kernels
+        sc = sc.requires_grad_(True)
+        out, loss, grads = self.step(sc, *rays)
+        done = torch.cuda.Event()
+        done.record(cur)
+        with torch.cuda.stream(self.copy_stream):         # D2H of the result off the compute stream
+            self.copy_stream.wait_event(done)
+            img = out["comp_rgb"].detach()
+            img.record_stream(self.copy_stream)
+            img_h = img.to("cpu", non_blocking=True)
+            loss_h = loss.detach().to("cpu", non_blocking=True)
+        return img_h, loss_h
 
     def h2d_bytes(self):
         return sum(t.numel() * 4 for t in [self.sc_h] + self.rays_h)

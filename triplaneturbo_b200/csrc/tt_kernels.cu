@@ -108,7 +108,7 @@ static int launch_geo_decoder(const float* planes, const float* wpack, const tt_
         if (int e = set_smem(k_geo_ws<kC, NORMAL>, smw)) return e;
         const int64_t ctas = (N + WS_CG * TC_GROUP - 1) / (WS_CG * TC_GROUP);
         const unsigned grid = (unsigned)(ctas < (int64_t)num_sms() ? (ctas < 1 ? 1 : ctas) : num_sms());
-        TT_LAUNCH((k_geo_ws<kC, NORMAL>), grid, WS_THREADS, smw, st, planes, wpack, *cfg, src, N, sdf, sdf_orig, grad, normal, masks, vscratch);
+        TT_LAUNCH((k_geo_ws<kC, NORMAL>), grid, WS_GEO_THREADS, smw, st, planes, wpack, *cfg, src, N, sdf, sdf_orig, grad, normal, masks, vscratch);
         return check_launch("k_geo_ws");
     }
     const size_t smg = (size_t)GeoSmem<kC, NORMAL>::TOTAL * 4;

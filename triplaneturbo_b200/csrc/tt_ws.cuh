@@ -48,10 +48,20 @@ constexpr int WS_NBUF = 2;                              // stage buffers per con
 // 65536 / 384 -> 168 registers per thread; the gather warpgroup grows to WS_REG_M (more loads in flight: the gather is
 // bound by loads in flight, tools/tma_gather_probe.cu), the two consumer warpgroups shrink to WS_REG_C.
 // 128 * 232 + 256 * 136 = 64512 = 384 * 168.
+#ifndef WS_GEO_NMG
+#define WS_GEO_NMG 1            // gather warpgroups of k_geo_ws: 1 (serves both consumer groups in turn) or 2 (one per consumer group)
+#endif
 #ifndef WS_REG_M
+#if WS_GEO_NMG == 2             // 512 threads start with 128 registers: 2 * 128 * (152 + 104) = 65536
+#define WS_REG_M 152
+#define WS_REG_C 104
+#else
 #define WS_REG_M 232
 #define WS_REG_C 136
 #endif
+#endif
+constexpr int WS_GEO_MT = WS_GEO_NMG * 128;                       // gather threads of k_geo_ws
+constexpr int WS_GEO_THREADS = WS_GEO_MT + WS_CG * TC_GROUP;
 #ifndef WS_GATHER_JB
 #define WS_GATHER_JB 3          // items (12 loads each) in flight per gather lane
 #endif
@@ -113,7 +123,7 @@ struct GeoWs {
     static constexpr int TAP_CY = TAP_CX + (NORMAL ? 128 * 12 : 0), PBASE = TAP_CY + (NORMAL ? 128 * 12 : 0);
     static constexpr int MTAB_FLOATS = PBASE + 128;
     // per consumer group: meta (id, x) and the blended encodings of its next tile
-    static constexpr int GROUP0 = MTAB + MTAB_FLOATS;
+    static constexpr int GROUP0 = MTAB + WS_GEO_NMG * MTAB_FLOATS;
     static constexpr int META = 0, STAGE = META + 128 * 4, GROUP_FLOATS = STAGE + 128 * SP;
     static constexpr int BARS = GROUP0 + WS_CG * GROUP_FLOATS;     // uint64: full, stage_free, mma per group
     static constexpr int TOTAL = BARS + 2 * 3 * WS_CG + 4;
@@ -188,7 +198,7 @@ __device__ __forceinline__ void ws_point_from_raw(const TcSrc& s, const WsRaw& r
 // SDF decoder (+ analytic normal) at a list of points.  Sources and outputs as k_geo_tc (tt_tc.cuh); vscratch:
 // ws_vscratch_floats(gridDim.x, C) floats (NORMAL only).
 template <int C, bool NORMAL>
-__global__ void __launch_bounds__(WS_THREADS, 1) k_geo_ws(const float* __restrict__ planes, const float* __restrict__ wp,
+__global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __restrict__ planes, const float* __restrict__ wp,
                                                          tt_config cfg, TcSrc src, int64_t N, float* sdf_o,
                                                          float* sdf_orig_o, float* grad_o, float* normal_o,
                                                          uint64_t* masks_o, float* __restrict__ vscratch) {
@@ -197,11 +207,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_geo_ws(const float* __restric
     constexpr int SP = L::SP, CP = L::CP, U = L::U;
     const int tid = threadIdx.x, warp = tid >> 5;
     const WOff wo = woff(C);
-    btile_fill(smem + L::W1H, smem + L::W1L, 64, C, [&](int n, int k) { return __ldg(wp + wo.w1s + n * C + k); }, tid, WS_THREADS);
-    btile_fill(smem + L::W2H, smem + L::W2L, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2s + n * 64 + k); }, tid, WS_THREADS);
+    btile_fill(smem + L::W1H, smem + L::W1L, 64, C, [&](int n, int k) { return __ldg(wp + wo.w1s + n * C + k); }, tid, WS_GEO_THREADS);
+    btile_fill(smem + L::W2H, smem + L::W2L, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2s + n * 64 + k); }, tid, WS_GEO_THREADS);
     if (NORMAL) {
-        btile_fill(smem + L::W2TH, smem + L::W2TL, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2s + k * 64 + n); }, tid, WS_THREADS);
-        btile_fill(smem + L::W1TH, smem + L::W1TL, CP, 64, [&](int n, int k) { return n < C ? __ldg(wp + wo.w1s + k * C + n) : 0.f; }, tid, WS_THREADS);
+        btile_fill(smem + L::W2TH, smem + L::W2TL, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2s + k * 64 + n); }, tid, WS_GEO_THREADS);
+        btile_fill(smem + L::W1TH, smem + L::W1TL, CP, 64, [&](int n, int k) { return n < C ? __ldg(wp + wo.w1s + k * C + n) : 0.f; }, tid, WS_GEO_THREADS);
     }
     if (tid < 64) smem[L::W3 + tid] = __ldg(wp + wo.w3s + tid);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BARS);
@@ -221,26 +231,30 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_geo_ws(const float* __restric
     const int64_t n_tiles = (n_live + TC_GROUP - 1) / TC_GROUP;
     const int64_t tile_stride = (int64_t)gridDim.x * WS_CG;
     float* vcta = NORMAL ? vscratch + (size_t)blockIdx.x * WS_CG * 2 * L::VTILE : nullptr;
-    // job j of this CTA: consumer group j & 1, its tile number j >> 1
-    auto job_tile = [&](int64_t j) { return (int64_t)blockIdx.x * WS_CG + (j & 1) + (j >> 1) * tile_stride; };
+    // gather jobs.  One gather warpgroup: job j serves consumer group j & 1 with its tile number j >> 1.  Two: warpgroup m
+    // serves consumer group m, job j = its tile number j.
+    const int mgrp = tid / 128;                                                      // gather warpgroup (tid < WS_GEO_MT)
+    auto job_group = [&](int64_t j) { return WS_GEO_NMG == 2 ? mgrp : (int)(j & 1); };
+    auto job_num = [&](int64_t j) { return WS_GEO_NMG == 2 ? j : (j >> 1); };
+    auto job_tile = [&](int64_t j) { return (int64_t)blockIdx.x * WS_CG + job_group(j) + job_num(j) * tile_stride; };
 
-    if (tid < WS_M) {
+    if (tid < WS_GEO_MT) {
         // ============================================================================ gather warps
         ws_reg_inc<WS_REG_M>();
-        const int mt = tid;
-        float* tab = smem + L::MTAB;
+        const int mt = tid % 128;
+        float* tab = smem + L::MTAB + mgrp * L::MTAB_FLOATS;
         int* tap_o = reinterpret_cast<int*>(tab + L::TAP_O);
         float* tap_w = tab + L::TAP_W; float* tap_cx = tab + L::TAP_CX; float* tap_cy = tab + L::TAP_CY;
         uint32_t* pbase = reinterpret_cast<uint32_t*>(tab + L::PBASE);
-        const bool prof_m = blockIdx.x == 0 && mt == 0; (void)prof_m;
+        const bool prof_m = blockIdx.x == 0 && tid == 0; (void)prof_m;
         WS_T0(tm);
         // software pipeline over jobs: sample ids two jobs ahead, sample positions one job ahead (both are dependent
         // global loads whose latency would otherwise be exposed once per tile)
         WsRaw cur = ws_load_raw(src, ws_load_id(src, job_tile(0), mt, n_live, n_tiles));
         int id_next = ws_load_id(src, job_tile(1), mt, n_live, n_tiles);
         for (int64_t j = 0; job_tile(j) < n_tiles; ++j) {
-            const int g = (int)(j & 1);
-            const uint32_t par = (uint32_t)((j >> 1) & 1);
+            const int g = job_group(j);
+            const uint32_t par = (uint32_t)(job_num(j) & 1);
             float* gs = smem + L::GROUP0 + g * L::GROUP_FLOATS;
             const WsRaw nxt = ws_load_raw(src, id_next);                        // in flight during this job's gather
             id_next = ws_load_id(src, job_tile(j + 2), mt, n_live, n_tiles);
@@ -255,7 +269,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_geo_ws(const float* __restric
 #pragma unroll
                 for (int kk = 0; kk < 3; ++kk) tp[kk] = make_taps(p[plane_ax(kk)], p[plane_ay(kk)], cfg.R);
             }
-            group_sync(0);                          // every gather thread is done with the previous job's tables
+            group_sync(mgrp);                       // every gather thread is done with the previous job's tables
 #pragma unroll
             for (int kk = 0; kk < 3; ++kk) {
                 int4 o4; float4 w4;
@@ -279,7 +293,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_geo_ws(const float* __restric
             WS_ACC(0, tm, prof_m);
             *reinterpret_cast<float4*>(gs + L::META + mt * 4) =
                 make_float4(__uint_as_float((uint32_t)cur.id), cx_[0], cx_[1], cx_[2]);
-            group_sync(0);
+            group_sync(mgrp);
             // ---- cooperative gather: item = (point, 16-byte channel chunk); 2 items = 24 loads in flight per lane.
             // Blends the encoding e (-> stage) and, for the normal, the tangent rows V_a = d e / d x_a (-> L2 scratch).
             float* stage = gs + L::STAGE;
@@ -353,11 +367,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_geo_ws(const float* __restric
     } else {
         // ============================================================================ consumer groups
         ws_reg_dec<WS_REG_C>();
-        const int g = (tid - WS_M) / TC_GROUP, tg = (tid - WS_M) % TC_GROUP;
+        const int g = (tid - WS_GEO_MT) / TC_GROUP, tg = (tid - WS_GEO_MT) % TC_GROUP;
         Umma u;
         u.tmem = *tmem_slot + (uint32_t)g * TC_COLS_PER_GROUP;
         u.lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        u.mbar = smem_u32(mmab + g); u.phase = 0; u.group = 1 + g;
+        u.mbar = smem_u32(mmab + g); u.phase = 0; u.group = WS_GEO_NMG + g;
         const bool leader = tg == 0;
         const BTile bW1 = btile_make(smem + L::W1H, smem + L::W1L, 64, C);
         const BTile bW2 = btile_make(smem + L::W2H, smem + L::W2L, 64, 64);
