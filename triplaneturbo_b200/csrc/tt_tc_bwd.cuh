@@ -39,6 +39,76 @@ __device__ __forceinline__ void coop_scatter(float* __restrict__ gplanes, size_t
     }
 }
 
+// Fused scatter + gather over the SAME taps with the SAME weights (SDF backward: scatter de . w, gather e~ = sum w . texel).
+// Both use the item mapping of coop_gather, so a thread reads the de chunk of an item from the stage, issues the item's 12
+// loads, sends the item's 12 vector reductions while the loads are in flight, then blends and overwrites the chunk with e~:
+// the reduction stream and the load stream of a tile overlap instead of running one after the other, the tap tables are
+// read once, and no barrier is needed between the two (a thread only touches its own items' stage chunks).
+template <int C, int NPL>
+__device__ __forceinline__ void coop_scatter_gather(const float* __restrict__ planes, float* __restrict__ gplanes, size_t ps,
+                                                    const int* tap_o, const float* tap_w, const uint32_t* pbase, float* stage,
+                                                    int tg) {
+    constexpr int U = C / 4, NT = 4 * NPL, SP = C + 4, JB = TT_GATHER_LOADS / NT;
+#pragma unroll 1
+    for (int j0 = 0; j0 < U; j0 += JB) {
+        float4 v[JB][NT];
+        float w[JB][NT];
+        int o[JB][NT];
+        int sto[JB];
+        float4 dv[JB];
+        size_t pofs[JB];
+#pragma unroll
+        for (int b = 0; b < JB; ++b) {
+            const int j = j0 + b < U ? j0 + b : U - 1;
+            const int item = tg + TC_GROUP * j;
+            const int pt = item / U, ch = item - pt * U;
+            sto[b] = pt * SP + ch * 4;
+            dv[b] = *reinterpret_cast<const float4*>(stage + sto[b]);
+            pofs[b] = (size_t)pbase[pt] * 6 * ps + ch * 4;
+            const float* base = planes + pofs[b];
+#pragma unroll
+            for (int q = 0; q < NT; q += 4) {
+                const int4 o4 = *reinterpret_cast<const int4*>(tap_o + pt * NT + q);
+                const float4 w4 = *reinterpret_cast<const float4*>(tap_w + pt * NT + q);
+                const float* pb = base + (size_t)(q >> 2) * ps;
+                v[b][q] = ldg4(pb + (size_t)o4.x * C); v[b][q + 1] = ldg4(pb + (size_t)o4.y * C);
+                v[b][q + 2] = ldg4(pb + (size_t)o4.z * C); v[b][q + 3] = ldg4(pb + (size_t)o4.w * C);
+                w[b][q] = w4.x; w[b][q + 1] = w4.y; w[b][q + 2] = w4.z; w[b][q + 3] = w4.w;
+                o[b][q] = o4.x; o[b][q + 1] = o4.y; o[b][q + 2] = o4.z; o[b][q + 3] = o4.w;
+            }
+        }
+        if (gplanes) {
+#pragma unroll
+            for (int b = 0; b < JB; ++b) {
+                if (j0 + b >= U) continue;                   // tail batch repeats the last item: scatter it once
+                float* gb = gplanes + pofs[b];
+#pragma unroll
+                for (int q = 0; q < NT; ++q) {
+                    const float ww = w[b][q];
+                    if (ww != 0.f)
+                        red_add4(gb + (size_t)(q >> 2) * ps + (size_t)o[b][q] * C,
+                                 make_float4(dv[b].x * ww, dv[b].y * ww, dv[b].z * ww, dv[b].w * ww));
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < JB; ++b) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) {
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float ww = w[b][k * 4 + t]; const float4 q = v[b][k * 4 + t];
+                    s.x = fmaf(ww, q.x, s.x); s.y = fmaf(ww, q.y, s.y); s.z = fmaf(ww, q.z, s.z); s.w = fmaf(ww, q.w, s.w);
+                }
+                acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+            }
+            *reinterpret_cast<float4*>(stage + sto[b]) = acc;
+        }
+    }
+}
+
 // Run-length merged scatter.  The points of a tile are consecutive samples of a ray (ray-major lists); inside the band
 // the importance sampler concentrates on, ten or more consecutive samples fall into the same texel cell, so their
 // contributions to a texel are summed in registers and leave the SM as ONE vector reduction.  Thread (ch, r) owns the
@@ -224,23 +294,21 @@ k_bwd_geo_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
             for (int c = 0; c < C; c += 4)
                 *reinterpret_cast<float4*>(stage + tg * SP + c) = make_float4(de[c], de[c + 1], de[c + 2], de[c + 3]);
         }
-#ifndef TT_BWDGEO_LOCK_SCATTER
-#define TT_BWDGEO_LOCK_SCATTER 1
+#ifndef TT_BWDGEO_FUSED
+#define TT_BWDGEO_FUSED 1
 #endif
-#if TT_BWDGEO_LOCK_SCATTER
+#if TT_BWDGEO_FUSED
+        // d L / d texel = de . w  scattered and  e~ = sum w . texel  gathered in one pass over the taps
         mem_lock(mlock, leader, group);
+        coop_scatter_gather<C, 3>(planes, gplanes, ps, tap_o, tap_om, pbase, stage, tg);
 #else
-        group_sync(group);
-#endif
+        mem_lock(mlock, leader, group);
         // d L / d texel = de · ω  (plain scatter: with 12 tap slots the run-length merged variant measured 4 % slower on
         // the synthetic benchmark planes, whose noisy SDF spreads the fine samples; it wins for the 64-wide colour scatter)
         if (gplanes) coop_scatter<C, 3>(gplanes, ps, tap_o, tap_om, pbase, 0, stage, tg);
-#if TT_BWDGEO_LOCK_SCATTER
         group_sync(group);
-#else
-        mem_lock(mlock, leader, group);
-#endif
         coop_gather<C, 3>(planes, ps, tap_o, tap_om, pbase, 0, stage, tg);                    // ẽ = Σ ω · texel
+#endif
         mem_unlock(mlock, leader, group);
         {
             float e[C];
