@@ -399,7 +399,7 @@ def run_render(args, wl, rank, world, local, real_stdout):
     geo_fwd = (nimp * f_sdf + S * 2 * f_sdf) / 2.0
     flops_of = {"k_importance_sample": fl["sample"], "k_render_fwd": fl["fwd"], "k_bwd_geo": fl["bwd_geo"],
                 "k_bwd_tex": fl["bwd_tex"], "k_geo_tc": geo_fwd, "k_geo_ws": geo_fwd, "k_tex_tc": S * f_feat,
-                "k_tex_ws": S * f_feat, "k_bwd_geo_tc": S * 4 * f_sdf, "k_bwd_geo_ws": S * 4 * f_sdf,
+                "k_tex_ws": S * f_feat, "k_tex_tc1": S * f_feat, "k_bwd_geo_tc": S * 4 * f_sdf, "k_bwd_geo_ws": S * 4 * f_sdf,
                 "k_bwd_tex_tc": S * 3 * f_feat, "k_bwd_tex_ws": S * 3 * f_feat}
     cand = {k: v for k, v in kern_tot.items() if k in flops_of} or kern_tot
     dom = max(cand, key=cand.get)
@@ -411,7 +411,7 @@ def run_render(args, wl, rank, world, local, real_stdout):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(args.workload, {}).get(dom)
     except Exception:
         pass
-    fwd3 = dom in ("k_geo_tc", "k_tex_tc", "k_geo_ws", "k_tex_ws", "k_bwd_geo_ws")
+    fwd3 = dom in ("k_geo_tc", "k_tex_tc", "k_tex_tc1", "k_geo_ws", "k_tex_ws", "k_bwd_geo_ws")
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": kern_ms[dom], "kernel_share_of_step": kern_tot[dom] / ms_total,

@@ -137,6 +137,12 @@ static int launch_tex_decoder(const float* planes, const float* wpack, const tt_
         TT_LAUNCH(k_tex_ws<kC>, grid, WS_THREADS, smw, st, planes, wpack, *cfg, src, N, features, masks);
         return check_launch("k_tex_ws");
     }
+    const size_t sm1 = (size_t)Tex1Smem<kC>::TOTAL * 4;
+    if (g_impl == 2 && Tex1Smem<kC>::OK && sm1 <= kMaxSmem) {      // one gather per tile, three A operands in disjoint TMEM columns
+        if (int e = set_smem(k_tex_tc1<kC>, sm1)) return e;
+        TT_LAUNCH(k_tex_tc1<kC>, tc_grid(N), TC_THREADS, sm1, st, planes, wpack, *cfg, src, N, features, masks);
+        return check_launch("k_tex_tc1");
+    }
     const size_t smt = (size_t)TexSmem<kC>::TOTAL * 4;
     if (int e = set_smem(k_tex_tc<kC>, smt)) return e;
     TT_LAUNCH(k_tex_tc<kC>, tc_grid(N), TC_THREADS, smt, st, planes, wpack, *cfg, src, N, features, masks);

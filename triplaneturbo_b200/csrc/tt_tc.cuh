@@ -577,6 +577,173 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tex_tc(const float* __restric
     if (warp == 0) tmem_dealloc_warp(*tmem_slot, 512);
 }
 
+// ---- colour decoder, one gather per tile (C <= 32) ------------------------------------------------------------------------
+// k_tex_tc above walks the three texture planes one after the other: taps, barrier, 4-tap gather, barrier, put A, wait for
+// the previous plane's MMAs, barrier, issue -- three dependent round trips per tile before the first layer is done.  For
+// C <= 32 the three A operands fit into disjoint TMEM columns (hi_k = 2kC, lo_k = 2kC + C, accumulator at 192), so this
+// variant gathers all 12 taps of a point in ONE cooperative pass (24 loads in flight per lane like the geometry gather),
+// puts the three operands, and issues the three MMA chains behind a single barrier.
+template <int C>
+struct Tex1Smem {
+    static constexpr int SP3 = 3 * C + 4;
+    static constexpr uint32_t COL_D = 192, COL_LO2 = 96;            // layer 2: hi [0,64) lo [96,160)
+    static constexpr int W1H = 0, W1L = W1H + 3 * 64 * C, W2H = W1L + 3 * 64 * C, W2L = W2H + 4096, W3 = W2L + 4096;
+    static constexpr int GROUP0 = W3 + 192;
+    static constexpr int TAP_O = 0, TAP_W = TAP_O + 128 * 12, PBASE = TAP_W + 128 * 12, STAGE = PBASE + 128;
+    static constexpr int GROUP_FLOATS = STAGE + 128 * SP3;
+    static constexpr int TOTAL = GROUP0 + TC_GROUPS * GROUP_FLOATS + 16;
+    static constexpr bool OK = 6 * C <= 192;
+};
+
+template <int C>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tex_tc1(const float* __restrict__ planes, const float* __restrict__ wp,
+                                                          tt_config cfg, TcSrc src, int64_t N, float* feat_o,
+                                                          uint64_t* masks_o) {
+    TT_SHARED(smem);
+    using L = Tex1Smem<C>;
+    constexpr int SP3 = L::SP3, U = C / 4;
+    const int tid = threadIdx.x, group = tid / TC_GROUP, tg = tid % TC_GROUP, warp = tid >> 5;
+    const WOff wo = woff(C);
+    for (int k = 0; k < 3; ++k)
+        btile_fill(smem + L::W1H + k * 64 * C, smem + L::W1L + k * 64 * C, 64, C,
+                   [&](int n, int kk) { return __ldg(wp + wo.w1f + n * 3 * C + k * C + kk); }, tid, TC_THREADS);
+    btile_fill(smem + L::W2H, smem + L::W2L, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2f + n * 64 + k); }, tid, TC_THREADS);
+    if (tid < 192) smem[L::W3 + tid] = __ldg(wp + wo.w3f + tid);
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + L::GROUP0 + TC_GROUPS * L::GROUP_FLOATS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbars + TC_GROUPS);
+    if (tid == 0) for (int g = 0; g < TC_GROUPS; ++g) mbar_init(mbars + g);
+    if (warp == 0) tmem_alloc_warp(tmem_slot, 512);
+    async_proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    Umma u;
+    u.tmem = *tmem_slot + (uint32_t)group * TC_COLS_PER_GROUP;
+    u.lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    u.mbar = smem_u32(mbars + group); u.phase = 0; u.group = group;
+    const bool leader = tg == 0;
+    BTile bW1[3];
+    for (int k = 0; k < 3; ++k) bW1[k] = btile_make(smem + L::W1H + k * 64 * C, smem + L::W1L + k * 64 * C, 64, C);
+    const BTile bW2 = btile_make(smem + L::W2H, smem + L::W2L, 64, 64);
+    float* gs = smem + L::GROUP0 + group * L::GROUP_FLOATS;
+    int* tap_o = reinterpret_cast<int*>(gs + L::TAP_O);
+    float* tap_w = gs + L::TAP_W;
+    uint32_t* pbase = reinterpret_cast<uint32_t*>(gs + L::PBASE);
+    float* stage = gs + L::STAGE;
+    const float* w3 = smem + L::W3;
+    const size_t ps = (size_t)cfg.R * cfg.R * C;
+    const int64_t n_live = src.count ? (int64_t)*src.count : N;
+    const int64_t n_tiles = (n_live + TC_GROUP - 1) / TC_GROUP;
+
+    for (int64_t tile = (int64_t)blockIdx.x * TC_GROUPS + group; tile < n_tiles; tile += (int64_t)gridDim.x * TC_GROUPS) {
+        const int64_t slot = tile * TC_GROUP + tg;
+        const bool valid = slot < n_live;
+        const int64_t id = valid ? (src.index ? (int64_t)src.index[slot] : slot) : 0;
+        float p[3] = {0.f, 0.f, 0.f}; int prompt = 0;
+        if (valid) {
+            float x[3];
+            tc_point(src, id, x, prompt);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const Taps t = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
+            int4 o4; float4 w4;
+            const bool i0 = valid && t.o[0] >= 0, i1 = valid && t.o[1] >= 0, i2 = valid && t.o[2] >= 0, i3 = valid && t.o[3] >= 0;
+            o4.x = i0 ? t.o[0] : 0; o4.y = i1 ? t.o[1] : 0; o4.z = i2 ? t.o[2] : 0; o4.w = i3 ? t.o[3] : 0;
+            w4.x = i0 ? t.w[0] : 0.f; w4.y = i1 ? t.w[1] : 0.f; w4.z = i2 ? t.w[2] : 0.f; w4.w = i3 ? t.w[3] : 0.f;
+            *reinterpret_cast<int4*>(tap_o + tg * 12 + k * 4) = o4;
+            *reinterpret_cast<float4*>(tap_w + tg * 12 + k * 4) = w4;
+        }
+        pbase[tg] = (uint32_t)prompt;
+        group_sync(group);
+        {   // cooperative gather of the three texture planes: item = (point, chunk), 12 loads each, 2 items in flight
+            constexpr int JB = 2;
+#pragma unroll 1
+            for (int j0 = 0; j0 < U; j0 += JB) {
+                float4 v[JB][12];
+                int pt[JB], ch[JB];
+#pragma unroll
+                for (int b = 0; b < JB; ++b) {
+                    const int j = j0 + b < U ? j0 + b : U - 1;
+                    const int item = tg + TC_GROUP * j;
+                    pt[b] = item / U; ch[b] = item - pt[b] * U;
+                    const float* base = planes + ((size_t)pbase[pt[b]] * 6 + 3) * ps + ch[b] * 4;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int4 o4 = *reinterpret_cast<const int4*>(tap_o + pt[b] * 12 + k * 4);
+                        const float* pb = base + (size_t)k * ps;
+                        v[b][k * 4 + 0] = ldg4(pb + (size_t)o4.x * C); v[b][k * 4 + 1] = ldg4(pb + (size_t)o4.y * C);
+                        v[b][k * 4 + 2] = ldg4(pb + (size_t)o4.z * C); v[b][k * 4 + 3] = ldg4(pb + (size_t)o4.w * C);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < JB; ++b) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(tap_w + pt[b] * 12 + k * 4);
+                        const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+                        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float4 q = v[b][k * 4 + t];
+                            s.x = fmaf(ww[t], q.x, s.x); s.y = fmaf(ww[t], q.y, s.y); s.z = fmaf(ww[t], q.z, s.z); s.w = fmaf(ww[t], q.w, s.w);
+                        }
+                        *reinterpret_cast<float4*>(stage + pt[b] * SP3 + k * C + ch[b] * 4) = s;
+                    }
+                }
+            }
+        }
+        group_sync(group);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float e[C];
+#pragma unroll
+            for (int c = 0; c < C; c += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(stage + tg * SP3 + k * C + c);
+                e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
+            }
+            umma_put_A_ex<C>(u, e, (uint32_t)(k * 2 * C), (uint32_t)(k * 2 * C + C));
+        }
+        group_sync(group);
+        if (leader) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) umma_mma_ex<3>(u, bW1[k], C, k > 0, (uint32_t)(k * 2 * C), (uint32_t)(k * 2 * C + C), L::COL_D);
+            umma_commit(u);
+        }
+        umma_wait(u);
+        float d[64];
+        umma_get_D<64>(u, d, L::COL_D);
+        uint64_t m1 = 0, m2 = 0;
+        {
+            float h[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) { m1 |= (uint64_t)(d[j] > 0.f) << j; h[j] = fmaxf(d[j], 0.f); }
+            umma_put_A_ex<64>(u, h, 0u, L::COL_LO2);
+        }
+        group_sync(group);
+        if (leader) { umma_mma_ex<3>(u, bW2, 64, false, 0u, L::COL_LO2, L::COL_D); umma_commit(u); }
+        umma_wait(u);
+        umma_get_D<64>(u, d, L::COL_D);
+        float f[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            const float h = fmaxf(d[j], 0.f);
+            m2 |= (uint64_t)(d[j] > 0.f) << j;
+            f[0] = fmaf(h, w3[j], f[0]); f[1] = fmaf(h, w3[64 + j], f[1]); f[2] = fmaf(h, w3[128 + j], f[2]);
+        }
+        if (valid) {
+            if (feat_o) { feat_o[id * 3] = f[0]; feat_o[id * 3 + 1] = f[1]; feat_o[id * 3 + 2] = f[2]; }
+            if (masks_o) { masks_o[id * 4] = m1; masks_o[id * 4 + 1] = m2; }     // ReLU masks for the backward
+        }
+        group_sync(group);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_warp(*tmem_slot, 512);
+}
+
 // importance sampler, stage 2: proposal sdf [n_rays][n_imp] -> density -> cdf -> inverse-CDF draws -> sorted edges
 __global__ void __launch_bounds__(128) k_sampler_post(tt_config cfg, int64_t n_rays, int n_imp, int n_fine,
                                                      const float* __restrict__ sdf, const float* __restrict__ jit0,
