@@ -64,6 +64,9 @@ typedef struct {
     float near_plane, far_plane; /* yaml :145-146 */
     float render_step_size;  /* neus_volume_renderer.py:84-86 */
     int32_t flags;           /* TT_FLAG_* */
+    int32_t image_h, image_w; /* optional hint: the rays are [B][image_h][image_w] images (row-major pixels).  0 = unknown.
+                                 tt_render_bwd then visits the samples in PATCH order (4x4 neighbouring rays x 8 samples per
+                                 tile), which lets the scatter kernels merge the taps of a tile; results do not depend on it */
 } tt_config;
 #define TT_FLAG_PRECISE_BWD 2  /* tt_render_bwd / tt_geometry_bwd: run the colour decoder's backward layers as 3xTF32 (fp32-equivalent)
                                   instead of single-pass TF32; one 128-thread group per CTA fits then (slower) */
@@ -74,10 +77,15 @@ int tt_version(void);
 const char* tt_last_error(void);
 /* 1 if a CUDA device is usable by this library, else 0 (never falls back to the CPU). */
 int tt_device_ok(void);
-/* Kernel family: 1 (default) = tcgen05 tensor-core kernels (3xTF32, TMEM accumulators), 0 = SIMT fp32 reference
+/* Kernel family: 2 (default) = warp-specialised tcgen05 kernels, 1 = round-1 tcgen05 kernels (3xTF32, TMEM), 0 = SIMT fp32 reference
  * kernels.  Both are CUDA; parity tests run both. */
 int tt_set_impl(int impl);
 int tt_get_impl(void);
+/* Experiment switches of the backward (defaults are the measured-fastest settings):
+ *   "scatter"     -1 auto (default), 0 plain, 1 run-length merged, 2 tile-merged hidden-gradient scatter
+ *   "patch_lists"  0 (default) / 1: with tt_config.image_h/w set, tt_render_bwd visits the samples in 4x4-pixel patch order
+ * Initial values come from the environment (TT_SCATTER, TT_PATCH_LISTS).  Results are identical up to the summation order. */
+int tt_set_option(const char* name, int value);
 
 /* ---- decoder weights -----------------------------------------------------------------
  * Replaces: the nn.Linear parameters of VanillaMLP (threestudio/models/networks.py:67-104)

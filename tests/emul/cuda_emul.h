@@ -36,6 +36,9 @@ struct dim3 {
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) int4 { int x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct alignas(8) int2 { int x, y; };
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 
 namespace tt_emul {
 inline thread_local uint3_e threadIdx_, blockIdx_;
@@ -183,6 +186,7 @@ inline float atomicAdd(float* addr, float v) {
     return old;
 }
 inline int atomicAdd(int* addr, int v) { std::atomic_ref<int> r(*addr); return r.fetch_add(v); }
+inline int atomicCAS(int* addr, int expect, int desired) { return tt_emul::cas(addr, expect, desired); }
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline void __trap() { std::abort(); }

@@ -13,7 +13,8 @@ from triplaneturbo_b200 import _cabi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libtt_emul.so")
-SRC = [os.path.join(HERE, "..", "..", "triplaneturbo_b200", "csrc", f) for f in ("tt_kernels.cu", "tt_device.cuh")]
+import glob
+SRC = glob.glob(os.path.join(HERE, "..", "..", "triplaneturbo_b200", "csrc", "*.cu*"))      # every kernel source
 SRC += [os.path.join(HERE, "cuda_emul.h"), os.path.join(HERE, "..", "..", "include", "triplane_b200.h")]
 
 
@@ -55,6 +56,9 @@ class Emul:
         if inv_std is None:
             inv_std = float(np.exp(np.float32(0.4605) * np.float32(10.0)))
         return _cabi.TTConfig(C_, R, P, rays_per_cache, radius, bias, inv_std, car, near, far, step, flags)
+
+    def set_option(self, name, value):
+        self.ok(self.L.tt_set_option(name.encode(), int(value)), "set_option")
 
     def set_impl(self, impl):
         self.ok(self.L.tt_set_impl(impl), "set_impl")

@@ -21,7 +21,7 @@ class TTConfig(C.Structure):
     _fields_ = [("C", C.c_int32), ("R", C.c_int32), ("P", C.c_int32), ("rays_per_cache", C.c_int32),
                 ("radius", C.c_float), ("sdf_bias_radius", C.c_float), ("inv_std", C.c_float),
                 ("cos_anneal_ratio", C.c_float), ("near_plane", C.c_float), ("far_plane", C.c_float),
-                ("render_step_size", C.c_float), ("flags", C.c_int32)]
+                ("render_step_size", C.c_float), ("flags", C.c_int32), ("image_h", C.c_int32), ("image_w", C.c_int32)]
 
 
 _cfgp = C.POINTER(TTConfig)
@@ -33,6 +33,7 @@ SIGNATURES = {
     "tt_device_ok": (C.c_int, []),
     "tt_set_impl": (C.c_int, [C.c_int]),
     "tt_get_impl": (C.c_int, []),
+    "tt_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "tt_launch_count": (i64, []),
     "tt_profile_begin": (C.c_int, []),
     "tt_profile_end": (C.c_int, [C.c_char_p, C.c_size_t]),

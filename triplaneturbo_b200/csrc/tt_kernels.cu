@@ -8,6 +8,7 @@
 #include "tt_sampler.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -108,7 +109,7 @@ static int launch_geo_decoder(const float* planes, const float* wpack, const tt_
         if (int e = set_smem(k_geo_ws<kC, NORMAL>, smw)) return e;
         const int64_t ctas = (N + WS_CG * TC_GROUP - 1) / (WS_CG * TC_GROUP);
         const unsigned grid = (unsigned)(ctas < (int64_t)num_sms() ? (ctas < 1 ? 1 : ctas) : num_sms());
-        TT_LAUNCH((k_geo_ws<kC, NORMAL>), grid, WS_GEO_THREADS, smw, st, planes, wpack, *cfg, src, N, sdf, sdf_orig, grad, normal, masks, vscratch);
+        TT_LAUNCH((k_geo_ws<kC, NORMAL>), grid, WS_GEO_THREADS, smw, st, planes, wpack, *cfg, src, N, sdf, sdf_orig, grad, normal, masks, vscratch, (float*)nullptr);
         return check_launch("k_geo_ws");
     }
     const size_t smg = (size_t)GeoSmem<kC, NORMAL>::TOTAL * 4;
@@ -149,16 +150,27 @@ static int launch_tex_decoder(const float* planes, const float* wpack, const tt_
     return check_launch("k_tex_tc");
 }
 
-// colour backward: RL = run-length merged hidden-gradient scatter, P3 = 3xTF32 layers (TT_FLAG_PRECISE_BWD)
-template <int kC, bool RL, bool P3>
+// experiment switches (tt_set_option; initial values from the environment): "scatter" = -1 auto, 0 plain, 1 run-length,
+// 2 tile-merged hidden-gradient scatter; "patch_lists" = 1: patch-ordered sample lists when the image shape is known
+static int g_opt_scatter = -2, g_opt_patch = -1;
+static int scatter_mode() {
+    if (g_opt_scatter == -2) { const char* e = getenv("TT_SCATTER"); g_opt_scatter = e ? atoi(e) : -1; }
+    return g_opt_scatter;
+}
+static bool patch_mode() {
+    if (g_opt_patch < 0) { const char* e = getenv("TT_PATCH_LISTS"); g_opt_patch = e ? (atoi(e) != 0) : 0; }
+    return g_opt_patch != 0;
+}
+// colour backward: SC = scatter variant of the hidden gradient, P3 = 3xTF32 layers (TT_FLAG_PRECISE_BWD)
+template <int kC, int SC, bool P3>
 static int launch_bwd_tex(const float* planes, const float* wpack, const tt_config* cfg, const TcSrc& ts, int64_t N, int64_t tiles,
                           const float* gf, const uint64_t* tex_masks, float* hid, float* gw, cudaStream_t st) {
     constexpr int GT = BwdTexSmem<kC, P3>::G;
     const size_t smx = (size_t)BwdTexSmem<kC, P3>::TOTAL * 4;
     const int64_t ctas_t = (tiles + GT - 1) / GT;
     const unsigned grid_t = (unsigned)(ctas_t < (int64_t)num_sms() ? ctas_t : num_sms());
-    if (int e = set_smem((k_bwd_tex_tc<kC, RL, P3>), smx)) return e;
-    TT_LAUNCH((k_bwd_tex_tc<kC, RL, P3>), grid_t, GT * TC_GROUP, smx, st, planes, wpack, *cfg, ts, N, gf, tex_masks, hid, gw);
+    if (int e = set_smem((k_bwd_tex_tc<kC, SC, P3>), smx)) return e;
+    TT_LAUNCH((k_bwd_tex_tc<kC, SC, P3>), grid_t, GT * TC_GROUP, smx, st, planes, wpack, *cfg, ts, N, gf, tex_masks, hid, gw);
     return check_launch("k_bwd_tex_tc");
 }
 
@@ -854,6 +866,12 @@ int tt_profile_end(char* buf, size_t cap) {
 #endif
     return TT_OK;
 }
+int tt_set_option(const char* name, int value) {
+    if (!name) return fail(TT_E_ARG, "tt_set_option: null name%s", "");
+    if (!strcmp(name, "scatter")) { if (value < -1 || value > 2) return fail(TT_E_ARG, "tt_set_option: scatter must be -1..2%s", ""); g_opt_scatter = value; return TT_OK; }
+    if (!strcmp(name, "patch_lists")) { g_opt_patch = value != 0; return TT_OK; }
+    return fail(TT_E_ARG, "tt_set_option: unknown option '%s'", name);
+}
 int tt_set_impl(int impl) {
     if (impl < 0 || impl > 2) return fail(TT_E_ARG, "tt_set_impl: impl must be 0 (SIMT), 1 (round-1 tcgen05) or 2 (warp-specialised tcgen05)%s", "");
     g_impl = impl;
@@ -937,9 +955,18 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
                 TcSrc src{}; src.mode = points ? 0 : 3; src.points = points; src.M = M; src.grid_res = grid_res;
                 if (sdf || sdf_orig || want_n || deformation) {
                     if (deformation) {      // field query of the mesh paths: SDF + deformation decoders on one gather
+                        const size_t smw_d = (size_t)GeoWs<kC, false, true>::TOTAL * 4;
+                        if (g_impl == 2 && smw_d <= kMaxSmem) {
+                            if (int e = set_smem((k_geo_ws<kC, false, true>), smw_d)) return e;
+                            const int64_t ctas = (N + WS_CG * TC_GROUP - 1) / (WS_CG * TC_GROUP);
+                            const unsigned grid = (unsigned)(ctas < (int64_t)num_sms() ? (ctas < 1 ? 1 : ctas) : num_sms());
+                            TT_LAUNCH((k_geo_ws<kC, false, true>), grid, WS_GEO_THREADS, smw_d, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, (float*)nullptr, (float*)nullptr, (uint64_t*)nullptr, (float*)nullptr, deformation);
+                            if (int e = check_launch("k_geo_ws")) return e;
+                        } else {
                         if (int e = set_smem(k_geo_tc<kC, false, true>, smg_d)) return e;
                         TT_LAUNCH((k_geo_tc<kC, false, true>), tc_grid(N), TC_THREADS, smg_d, (cudaStream_t)stream, planes, wpack, *cfg, src, N, sdf, sdf_orig, sdf_grad, normal, (uint64_t*)nullptr, deformation);
                         if (int e = check_launch("k_geo_tc")) return e;
+                        }
                     } else if (want_n) {
                         if (int e = launch_geo_decoder<kC, true>(planes, wpack, cfg, src, N, sdf, sdf_orig, sdf_grad, normal, nullptr, nullptr, (cudaStream_t)stream)) return e;
                     } else {
@@ -1114,12 +1141,21 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
                     // colour branch: per-sample kernel scatters the 64-wide hidden gradient, then two dense products
                     if (cudaMemsetAsync(hid, 0, hid_floats(cfg) * sizeof(float), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
                     ts.index = tex_list; ts.count = tex_count;
-                    const bool rl = !src.points && src.rs.S >= 256;        // long rays: consecutive samples share texel cells
+                    // scatter of the hidden gradient: run-length merged for long rays (consecutive samples share texel cells),
+                    // plain otherwise; TT_SCATTER=0|1|2 forces plain / run-length / tile-merged (the
+                    // tile-merged form cuts the reductions 4-6x on patch-ordered lists but costs as many issue slots as it saves)
+                    int sc = scatter_mode();
+                    if (sc < 0) sc = (!src.points && src.rs.S >= 256) ? 1 : 0;
+                    if ((int64_t)cfg->P * 3 * cfg->R * cfg->R >= (1LL << MergeWs::KEY_BITS) && sc == 2) sc = 0;       // texel numbers must fit the merge keys
                     const bool p3 = (cfg->flags & TT_FLAG_PRECISE_BWD) != 0 && (size_t)BwdTexSmem<kC, true>::TOTAL * 4 <= kMaxSmem;
-                    if (p3) { if (int e = rl ? launch_bwd_tex<kC, true, true>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)
-                                                 : launch_bwd_tex<kC, false, true>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)) return e; }
-                    else { if (int e = rl ? launch_bwd_tex<kC, true, false>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)
-                                              : launch_bwd_tex<kC, false, false>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)) return e; }
+                    int e = 0;
+                    if (p3) e = sc == 2 ? launch_bwd_tex<kC, 2, true>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)
+                              : sc == 1 ? launch_bwd_tex<kC, 1, true>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)
+                                        : launch_bwd_tex<kC, 0, true>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st);
+                    else e = sc == 2 ? launch_bwd_tex<kC, 2, false>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)
+                           : sc == 1 ? launch_bwd_tex<kC, 1, false>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st)
+                                     : launch_bwd_tex<kC, 0, false>(planes, wpack, cfg, ts, N, tiles, gf, tex_masks, hid, gw, st);
+                    if (e) return e;
                     if (gplanes) {
                         const size_t smh = (size_t)64 * kC * 4;
                         const int64_t items = (int64_t)cfg->P * cfg->R * cfg->R * (kC / 4);
@@ -1184,10 +1220,20 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
         geo_list = reinterpret_cast<int*>(scratch + 7 * N); tex_list = geo_list + N; counts = tex_list + N;
         if (cudaMemsetAsync(counts, 0, 2 * sizeof(int), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
     }
+    // rays given as [B][H][W] images: patch-ordered lists (k_patch_lists) so that the scatter kernels can merge a tile's taps
+    const bool patch_lists = geo_list && cfg->image_h > 0 && cfg->image_w > 0 && cfg->image_h % PATCH == 0 && cfg->image_w % PATCH == 0 &&
+                             n_rays % ((int64_t)cfg->image_h * cfg->image_w) == 0 && ray_chunks(S) <= PATCH_MAX_CHUNKS && patch_mode();
     TT_LAUNCH(k_render_bwd_comp, (unsigned)((n_rays + RAY_WARPS - 1) / RAY_WARPS), RAY_WARPS * 32, 0, st, *cfg, rst, n_rays, acc, sdf, sdf_grad, features,
         trans, g_acc, g_sdf, g_sdf_grad, g_normal, g_features, g_weights, rgb_grad_scale, gs, u, gf, g_inv_std,
-        geo_list, counts, tex_list, counts ? counts + 1 : (int*)nullptr, counts ? reinterpret_cast<uint32_t*>(counts + 16) : (uint32_t*)nullptr);
+        geo_list, counts, tex_list, counts ? counts + 1 : (int*)nullptr, counts ? reinterpret_cast<uint32_t*>(counts + 16) : (uint32_t*)nullptr,
+        patch_lists ? 0 : 1);
     if (int e = check_launch("k_render_bwd_comp")) return e;
+    if (patch_lists) {
+        const size_t smp = (size_t)(PATCH_RAYS * 2 * PATCH_MAX_CHUNKS + 16) * 4;
+        TT_LAUNCH(k_patch_lists, (unsigned)(n_rays / PATCH_RAYS), PATCH_THREADS, smp, st, (const uint32_t*)reinterpret_cast<uint32_t*>(counts + 16),
+                  (int)cfg->image_h, (int)cfg->image_w, S, geo_list, counts, tex_list, counts + 1);
+        if (int e = check_launch("k_patch_lists")) return e;
+    }
     if (!gplanes && !gw) return TT_OK;
     PtSrc src; src.points = nullptr; src.M = 0; src.rs = rs; src.rays_per_cache = cfg->rays_per_cache;
     float* hid = scratch + round4((size_t)N * 9 + 16 + (size_t)n_rays * 2 * (size_t)ray_chunks(S));

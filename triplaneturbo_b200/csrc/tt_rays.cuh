@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(RAY_WARPS * 32) k_render_bwd_comp(tt_config cf
         const float* __restrict__ g_sdf, const float* __restrict__ g_grad, const float* __restrict__ g_normal,
         const float* __restrict__ g_feat, const float* __restrict__ g_weights, float rgb_scale,
         float* __restrict__ gs_o, float* __restrict__ u_o, float* __restrict__ gf_o, float* g_inv_std,
-        int* geo_list, int* geo_count, int* tex_list, int* tex_count, uint32_t* flags) {
+        int* geo_list, int* geo_count, int* tex_list, int* tex_count, uint32_t* flags, int emit_lists) {
     const int lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * RAY_WARPS + (threadIdx.x >> 5);
     if (ray >= n_rays) return;
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(RAY_WARPS * 32) k_render_bwd_comp(tt_config cf
         gis = wsum_all(gis);
         if (lane == 0 && gis != 0.f) atomicAdd(g_inv_std, gis);
     }
-    if (fl) {           // ordered slices of the two lists
+    if (fl && emit_lists) {           // ordered slices of the two lists (ray order; patch order: k_patch_lists)
         __syncwarp();
         int at_g = warp_reserve(ng, geo_count, lane), at_t = warp_reserve(nt, tex_count, lane);
         for (int c = 0; c < NCH; ++c) {
@@ -300,6 +300,62 @@ __global__ void __launch_bounds__(RAY_WARPS * 32) k_render_bwd_comp(tt_config cf
             if ((mt >> lane) & 1u) tex_list[at_t + __popc(mt & lanes_below(lane))] = si;
             at_g += __popc(mg); at_t += __popc(mt);
         }
+    }
+}
+
+// ---- patch-ordered sample lists --------------------------------------------------------------------------------------------
+// When the rays are [B][H][W] images (tt_config.image_h/w), the lists of the samples the decoder backward visits are
+// emitted from the flag words of k_render_bwd_comp in PATCH order: CTA = a 4x4 patch of neighbouring pixels, entries ordered
+// (chunk of 8 consecutive samples, ray of the patch, sample of the chunk).  A 128-sample tile of the backward kernels is then
+// ~ 16 neighbouring rays x 8 samples, whose bilinear taps fall on few distinct texels (~8 taps per texel at config 3,
+// 1.5 in ray order): coop_scatter_merged (tt_tc_bwd.cuh) sums them on chip.  The patches reserve their slices with one
+// atomic per list, like the rays of the ray-ordered lists; the order of the entries never changes a result bit of the
+// forward and only the (already unordered) summation order of the float reductions in the backward.
+constexpr int PATCH = 4, PATCH_RAYS = PATCH * PATCH, PATCH_THREADS = 256, PATCH_MAX_CHUNKS = 32;
+__global__ void __launch_bounds__(PATCH_THREADS) k_patch_lists(const uint32_t* __restrict__ flags, int H, int W, int S,
+        int* geo_list, int* geo_count, int* tex_list, int* tex_count) {
+    TT_SHARED(smem);
+    uint32_t* fl_s = reinterpret_cast<uint32_t*>(smem);                 // [16 rays][2 NCH]
+    int* misc = reinterpret_cast<int*>(smem) + PATCH_RAYS * 2 * PATCH_MAX_CHUNKS;      // warp sums [8], base
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int NCH = ray_chunks(S), PW = W / PATCH, PH = H / PATCH;
+    const int img = blockIdx.x / (PH * PW), rem = blockIdx.x - img * PH * PW, py = rem / PW, px = rem - py * PW;
+    auto ray_of = [&](int r) { return ((int64_t)img * H + py * PATCH + r / PATCH) * W + px * PATCH + r % PATCH; };
+    for (int i = tid; i < PATCH_RAYS * 2 * NCH; i += PATCH_THREADS) {
+        const int r = i / (2 * NCH), w = i - r * 2 * NCH;
+        fl_s[i] = flags[ray_of(r) * 2 * NCH + w];
+    }
+    __syncthreads();
+    const int n8 = (S + 7) / 8, cells = n8 * PATCH_RAYS, K = (cells + PATCH_THREADS - 1) / PATCH_THREADS;
+    for (int which = 0; which < 2; ++which) {
+        int* list = which ? tex_list : geo_list; int* count = which ? tex_count : geo_count;
+        auto mask_of = [&](int q) -> uint32_t {          // cell q = (chunk of 8 samples, ray): its 8 flag bits
+            const int c8 = q / PATCH_RAYS, r = q - c8 * PATCH_RAYS;
+            return (fl_s[r * 2 * NCH + 2 * (c8 >> 2) + which] >> ((c8 & 3) * 8)) & 0xffu;
+        };
+        int sum = 0;
+        for (int i = 0; i < K; ++i) { const int q = tid * K + i; if (q < cells) sum += __popc(mask_of(q)); }
+        int v = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += o; }
+        if (lane == 31) misc[wrp] = v;
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int q = 0; q < PATCH_THREADS / 32; ++q) { const int t = misc[q]; misc[q] = tot; tot += t; }
+            misc[8] = tot > 0 ? atomicAdd(count, tot) : 0;
+        }
+        __syncthreads();
+        int at = misc[8] + misc[wrp] + v - sum;
+        for (int i = 0; i < K; ++i) {
+            const int q = tid * K + i;
+            if (q >= cells) break;
+            const int c8 = q / PATCH_RAYS, r = q - c8 * PATCH_RAYS;
+            uint32_t m = mask_of(q);
+            const int64_t si0 = ray_of(r) * S + c8 * 8;
+            while (m) { const int b = __ffs(m) - 1; m &= m - 1; list[at++] = (int)(si0 + b); }
+        }
+        __syncthreads();
     }
 }
 

@@ -16,6 +16,22 @@
 
 namespace tt {
 
+// Optional phase anatomy (-DTT_WS_TIMING): thread 0 of the gather warps and thread 0 of consumer group 0 of CTA 0 accumulate
+// the cycles they spend in each phase into g_ws_prof (read back with tt_debug_ws_prof).
+#if defined(TT_WS_TIMING) && !defined(TT_EMUL)
+__device__ unsigned long long g_ws_prof[32];
+__device__ __forceinline__ void g_ws_prof_tiles() { g_ws_prof[16] += 1; }
+__device__ __forceinline__ void g_ws_prof_add(int slot, unsigned long long v) { g_ws_prof[slot] += v; }
+#define WS_T0(var) long long var = clock64()
+#define WS_ACC(slot, var, cond) do { if (cond) { const long long n_ = clock64(); g_ws_prof[slot] += (unsigned long long)(n_ - var); var = n_; } } while (0)
+#else
+__device__ __forceinline__ void g_ws_prof_tiles() {}
+__device__ __forceinline__ void g_ws_prof_add(int, unsigned long long) {}
+#define WS_T0(var)
+#define WS_ACC(slot, var, cond)
+#endif
+
+
 template <int C, int NPL>
 __device__ __forceinline__ void coop_scatter(float* __restrict__ gplanes, size_t ps, const int* tap_o, const float* tap_w,
                                              const uint32_t* pbase, int plane0, const float* stage, int tg) {
@@ -164,6 +180,143 @@ __device__ __forceinline__ void coop_scatter_rl(float* __restrict__ dst, size_t 
 #pragma unroll
     for (int s = 0; s < NT; ++s)
         if (cur[s] >= 0) red_add4(base + (size_t)(s >> 2) * plane_stride + (size_t)cur[s] * texel_stride, acc[s]);
+}
+
+
+// ---- tile-merged scatter -------------------------------------------------------------------------------------------------
+// The taps of a tile that fall on the SAME texel are summed inside the SM first: one vector reduction per (texel, 16-byte
+// chunk) instead of one per (tap, chunk).  The scatter phases run at the L2 reduction rate, so the number of
+// reductions is what they cost; with the patch-ordered sample lists (k_patch_lists: a tile = 4x4 neighbouring rays x 8
+// consecutive samples) a texel receives ~8 of a tile's taps (measured on the config-3 samples), ~1.5 in ray order.
+//   1. every thread inserts the texels of its point's taps into an open-addressing hash table in shared memory
+//      (key = global texel number) and takes a rank inside the texel's bucket;
+//   2. a scan over the table turns the bucket sizes into list offsets and compacts the used buckets;
+//   3. the taps are written to their bucket's list;
+//   4. item = (used bucket, 16-byte chunk): sum weight x staged row over the bucket's taps, ONE red.global.add.v4.f32.
+// Workspace: MergeWs::TOTAL ints of shared memory per group (aliases an operand tile that is free during the scatter).
+struct MergeWs {
+    static constexpr int HN = 2048, MAXT = 1536;                 // hash positions; taps of a tile (128 points x 3 planes x 4)
+    static constexpr int KEY = 0, CNT = KEY + HN, ENT = CNT + HN, MISC = ENT + 2 * MAXT + 16;
+    static constexpr int TOTAL = MISC + 8;
+    static constexpr int KEY_BITS = 24;                          // texel numbers must fit (the point index rides above them)
+};
+// key(k, t) / weight(k, t): texel number (prompt, plane and offset folded: the destination row is dst + key * texel_stride)
+// and weight of tap t of plane k of THIS thread's point; weight 0 = no tap.
+template <int CH, int NPL, typename KeyF, typename WF>
+__device__ __forceinline__ void coop_scatter_merged(float* __restrict__ dst, int texel_stride, int* ws, const float* stage,
+                                                    int stage_stride, int tg, int group, KeyF key_of, WF w_of) {
+    constexpr int NT = NPL * 4, HN = MergeWs::HN, KB = MergeWs::KEY_BITS;
+    static_assert(128 * NT <= MergeWs::MAXT, "workspace");
+    static_assert(TC_GROUP % CH == 0, "ranges");
+    int* hkey = ws + MergeWs::KEY; int* hcnt = ws + MergeWs::CNT;
+    int2* ent = reinterpret_cast<int2*>(ws + MergeWs::ENT);           // bucket after bucket: (texel | point << 24, weight)
+    int* misc = ws + MergeWs::MISC;
+    const bool prof = blockIdx.x == 0 && threadIdx.x == 0; (void)prof;
+    WS_T0(tm_);
+    for (int i = tg * 4; i < HN; i += TC_GROUP * 4) {
+        *reinterpret_cast<int4*>(hkey + i) = make_int4(-1, -1, -1, -1);
+        *reinterpret_cast<int4*>(hcnt + i) = make_int4(0, 0, 0, 0);
+    }
+    group_sync(group);
+    WS_ACC(24, tm_, prof);
+    // (the three passes keep the shared-memory atomics of the 12 taps independent of each other: they pipeline)
+    int hpos[NT], aux[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        hpos[j] = -1; aux[j] = 0;
+        if (w_of(j >> 2, j & 3) != 0.f) {
+            const int key = key_of(j >> 2, j & 3);
+            hpos[j] = (int)(((uint32_t)key * 2654435761u) >> 21);
+            aux[j] = atomicCAS(hkey + hpos[j], -1, key);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        if (hpos[j] >= 0 && aux[j] != -1) {
+            const int key = key_of(j >> 2, j & 3);
+            int old = aux[j];
+            while (old != -1 && old != key) {                     // linear probing
+                hpos[j] = (hpos[j] + 1) & (HN - 1);
+                old = atomicCAS(hkey + hpos[j], -1, key);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) aux[j] = hpos[j] >= 0 ? atomicAdd(hcnt + hpos[j], 1) : 0;       // rank in the bucket
+    group_sync(group);
+    WS_ACC(25, tm_, prof);
+    {   // exclusive scan of the bucket sizes = offsets of the buckets in the entry list, 16 positions per thread
+        constexpr int PER = HN / TC_GROUP;
+        int c[PER], s = 0;
+#pragma unroll
+        for (int i = 0; i < PER; i += 4) {
+            const int4 q = *reinterpret_cast<const int4*>(hcnt + tg * PER + i);
+            c[i] = q.x; c[i + 1] = q.y; c[i + 2] = q.z; c[i + 3] = q.w;
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) s += c[i];
+        int v = s;
+        const int lane = tg & 31, wrp = tg >> 5;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += o; }
+        if (lane == 31) misc[wrp] = v;
+        group_sync(group);
+        int off = v - s;
+        for (int q = 0; q < wrp; ++q) off += misc[q];
+#pragma unroll
+        for (int i = 0; i < PER; i += 4) {
+            int4 q;
+            q.x = off; off += c[i]; q.y = off; off += c[i + 1]; q.z = off; off += c[i + 2]; q.w = off; off += c[i + 3];
+            *reinterpret_cast<int4*>(hcnt + tg * PER + i) = q;
+        }
+        if (tg == TC_GROUP - 1) misc[4] = off;            // entries of the tile
+    }
+    group_sync(group);
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+        if (hpos[j] >= 0)
+            ent[hcnt[hpos[j]] + aux[j]] = make_int2(key_of(j >> 2, j & 3) | (tg << KB), (int)__float_as_uint(w_of(j >> 2, j & 3)));
+    group_sync(group);
+    WS_ACC(26, tm_, prof);
+    // The entry list is cut into TC_GROUP / CH equal ranges; thread (range, 16-byte chunk) walks its range, sums weight x
+    // staged row while the texel stays the same and issues ONE vector reduction per run (a bucket that straddles two
+    // ranges costs two).  Entries are read four at a time: their loads do not depend on the running sum.
+    {
+        constexpr int NRANGE = TC_GROUP / CH;
+        const int total = misc[4];
+        if (prof) g_ws_prof_add(28, (unsigned long long)total);
+        const int r = tg / CH, ch = tg - r * CH;
+        const int e0 = (int)(((long long)total * r) / NRANGE), e1 = (int)(((long long)total * (r + 1)) / NRANGE);
+        int cur = -1;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* srow = stage + ch * 4;
+        float* drow = dst + ch * 4;
+#pragma unroll 1
+        for (int e = e0; e < e1; e += 4) {
+            int2 en[4]; float4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) en[q] = ent[e + q < e1 ? e + q : e1 - 1];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const float4*>(srow + ((uint32_t)en[q].x >> KB) * stage_stride);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (e + q < e1) {
+                    const int key = en[q].x & ((1 << KB) - 1);
+                    const float w = __uint_as_float((uint32_t)en[q].y);
+                    if (key != cur) {
+                        if (cur >= 0) red_add4(drow + (size_t)cur * texel_stride, acc);
+                        cur = key; acc = make_float4(w * v[q].x, w * v[q].y, w * v[q].z, w * v[q].w);
+                    } else {
+                        acc.x = fmaf(w, v[q].x, acc.x); acc.y = fmaf(w, v[q].y, acc.y);
+                        acc.z = fmaf(w, v[q].z, acc.z); acc.w = fmaf(w, v[q].w, acc.w);
+                    }
+                }
+            }
+        }
+        if (cur >= 0) red_add4(drow + (size_t)cur * texel_stride, acc);
+    }
+    group_sync(group);
+    WS_ACC(27, tm_, prof);
 }
 
 // ================================================================================================ SDF branch
@@ -411,7 +564,9 @@ struct BwdTexSmem {
 
 // RL: run-length merged scatter of the hidden gradient (wins when many consecutive samples of a ray share texel cells:
 // config 2, 289 samples per ray: 109 vs 113 ms) or the plain one (config 3, 193 samples per ray at 512^2: 432 vs 460 ms).
-template <int C, bool RL, bool P3>
+// SC: 0 plain, 1 run-length merged, 2 tile-merged (coop_scatter_merged; its workspace aliases the A tile of the dW2
+// contraction, whose MMAs have completed before the scatter)
+template <int C, int SC, bool P3>
 __global__ void __launch_bounds__(BwdTexSmem<C, P3>::G * TC_GROUP, 1)
 k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_config cfg, TcSrc src, int64_t N,
              const float* __restrict__ gf_i, const uint64_t* __restrict__ masks, float* __restrict__ hid,
@@ -476,6 +631,8 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
     float dw3[3] = {0.f, 0.f, 0.f};            // dW3[c][j] partial: j = tg & 63 over the points of half tg >> 6
     const int j3 = tg & 63, half3 = tg >> 6;
 
+    const bool prof = blockIdx.x == 0 && tid == 0; (void)prof;
+    WS_T0(tp_);
     for (int64_t tile = (int64_t)blockIdx.x * G + group; tile < n_tiles; tile += (int64_t)gridDim.x * G) {
         const int64_t slot = tile * TC_GROUP + tg;
         const bool valid = slot < n_live;
@@ -483,6 +640,7 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
         float gf[3] = {0.f, 0.f, 0.f};
         if (valid) { gf[0] = gf_i[id * 3]; gf[1] = gf_i[id * 3 + 1]; gf[2] = gf_i[id * 3 + 2]; }
         const bool active = valid && (gf[0] != 0.f || gf[1] != 0.f || gf[2] != 0.f);
+        if (prof) g_ws_prof_tiles();
         // the ReLU masks are the forward's (3xTF32) masks: a single-pass recompute may flip units near zero
         const uint64_t m1 = active ? masks[id * 4] : 0ull, m2 = active ? masks[id * 4 + 1] : 0ull;
         int prompt = 0;
@@ -496,6 +654,7 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
         pbase[tg] = (uint32_t)prompt;
         gfs[tg] = gf[0]; gfs[128 + tg] = gf[1]; gfs[256 + tg] = gf[2];
         float d[64];
+        WS_ACC(20, tp_, prof);
         // ---- recompute (single pass): z1 = Σ_k W1f_k e_k, z2 = W2f relu(z1) -----------------------------------------
 #pragma unroll 1
         for (int k = 0; k < 3; ++k) {
@@ -525,6 +684,7 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
         }
         umma_wait(u);
         umma_get_D<64>(u, d);
+        WS_ACC(21, tp_, prof);
         // ---- g2 = m2 ⊙ W3ᵀ gf needs only the masks: dW2 += g2 h1ᵀ is issued together with z2 = W2 h1 ------------------
         {
             float h[64];
@@ -584,7 +744,18 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
             *reinterpret_cast<float4*>(stage + tg * HS + j) =
                 make_float4(((m1 >> j) & 1ull) ? g1[j] : 0.f, ((m1 >> (j + 1)) & 1ull) ? g1[j + 1] : 0.f,
                             ((m1 >> (j + 2)) & 1ull) ? g1[j + 2] : 0.f, ((m1 >> (j + 3)) & 1ull) ? g1[j + 3] : 0.f);
+        WS_ACC(22, tp_, prof);
         // ---- scatter g1 · w into the hidden-gradient planes ----------------------------------------------------------
+        if (SC == 2) {
+            static_assert(MergeWs::TOTAL <= wg_tile_floats(64), "merge workspace must fit in the A tile");
+            Taps t3[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) t3[k] = make_taps(p[plane_ax(k)], p[plane_ay(k)], cfg.R);
+            const int kbase = prompt * 3 * cfg.R * cfg.R, rr = cfg.R * cfg.R;
+            coop_scatter_merged<16, 3>(hid, 64, reinterpret_cast<int*>(At), stage, HS, tg, group,
+                [&](int k, int t) { return kbase + k * rr + t3[k].o[t]; },
+                [&](int k, int t) { return (active && t3[k].o[t] >= 0) ? t3[k].w[t] : 0.f; });
+        } else
 #pragma unroll 1
         for (int k = 0; k < 3; ++k) {
             {
@@ -598,7 +769,7 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
                 *reinterpret_cast<float4*>(tap_w + tg * 4) = w4;
             }
             group_sync(group);
-            if (RL) coop_scatter_rl<16, 1>(hid + (size_t)k * hs, 3 * hs, 0, 64, tap_o, tap_w, pbase, stage, HS, tg);
+            if (SC == 1) coop_scatter_rl<16, 1>(hid + (size_t)k * hs, 3 * hs, 0, 64, tap_o, tap_w, pbase, stage, HS, tg);
             else {   // plain scatter of the 64-wide hidden gradient: item = (point, 16-byte chunk), 4 vector reductions each
 #pragma unroll 4
                 for (int j = 0; j < 16; ++j) {
@@ -616,6 +787,7 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
             }
             group_sync(group);
         }
+        WS_ACC(23, tp_, prof);
         any_tile = true;
     }
     tc_fence_before();

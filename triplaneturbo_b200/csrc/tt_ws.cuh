@@ -27,19 +27,6 @@
 
 namespace tt {
 
-// Optional phase anatomy (-DTT_WS_TIMING): thread 0 of the gather warps and thread 0 of consumer group 0 of CTA 0 accumulate
-// the cycles they spend in each phase into g_ws_prof (read back with tt_debug_ws_prof).
-#if defined(TT_WS_TIMING) && !defined(TT_EMUL)
-__device__ unsigned long long g_ws_prof[32];
-__device__ __forceinline__ void g_ws_prof_tiles() { g_ws_prof[16] += 1; }
-#define WS_T0(var) long long var = clock64()
-#define WS_ACC(slot, var, cond) do { if (cond) { const long long n_ = clock64(); g_ws_prof[slot] += (unsigned long long)(n_ - var); var = n_; } } while (0)
-#else
-__device__ __forceinline__ void g_ws_prof_tiles() {}
-#define WS_T0(var)
-#define WS_ACC(slot, var, cond)
-#endif
-
 constexpr int WS_M = 128;                               // gather threads
 constexpr int WS_CG = 2;                                // consumer groups
 constexpr int WS_THREADS = WS_M + WS_CG * TC_GROUP;     // 384
@@ -109,14 +96,21 @@ __device__ __forceinline__ uint32_t ws_pos_bits(const float (&d)[32]) {
 // all-ones / all-zeros word from bit j of m
 __device__ __forceinline__ uint32_t ws_bit_mask(uint32_t m, int j) { return 0u - ((m >> j) & 1u); }
 
-template <int C, bool NORMAL>
+// DEFORM (field query of the mesh paths, forward_field): the deformation decoder runs on the same encoding.  Its first
+// layer is STACKED under the SDF decoder's ([128][C] weight tile, one N = 128 MMA chain, accumulator columns [128,256)), so a
+// tile costs three layer round trips instead of four.
+template <int C, bool NORMAL, bool DEFORM = false>
 struct GeoWs {
+    static_assert(!(NORMAL && DEFORM), "the field query has no normal");
     static constexpr int SP = C + 4, CP = (C + 15) / 16 * 16, U = C / 4;
+    static constexpr int N1 = DEFORM ? 128 : 64;            // rows of the first-layer weight tile
     // float offsets: weight tiles (tf32 hi / lo, canonical K-major)
-    static constexpr int W1H = 0, W1L = W1H + 64 * C, W2H = W1L + 64 * C, W2L = W2H + 4096;
+    static constexpr int W1H = 0, W1L = W1H + N1 * C, W2H = W1L + N1 * C, W2L = W2H + 4096;
     static constexpr int W2TH = W2L + 4096, W2TL = W2TH + (NORMAL ? 4096 : 0);
     static constexpr int W1TH = W2TL + (NORMAL ? 4096 : 0), W1TL = W1TH + (NORMAL ? CP * 64 : 0);
-    static constexpr int W3 = W1TL + (NORMAL ? CP * 64 : 0);
+    static constexpr int W2DH = W1TL + (NORMAL ? CP * 64 : 0), W2DL = W2DH + (DEFORM ? 4096 : 0);
+    static constexpr int W3D = W2DL + (DEFORM ? 4096 : 0);
+    static constexpr int W3 = W3D + (DEFORM ? 192 : 0);
     // gather-group tables of the tile being gathered
     static constexpr int MTAB = W3 + 64;
     static constexpr int TAP_O = 0, TAP_W = TAP_O + 128 * 12, TAP_CX = TAP_W + 128 * 12;
@@ -197,18 +191,24 @@ __device__ __forceinline__ void ws_point_from_raw(const TcSrc& s, const WsRaw& r
 
 // SDF decoder (+ analytic normal) at a list of points.  Sources and outputs as k_geo_tc (tt_tc.cuh); vscratch:
 // ws_vscratch_floats(gridDim.x, C) floats (NORMAL only).
-template <int C, bool NORMAL>
+template <int C, bool NORMAL, bool DEFORM = false>
 __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __restrict__ planes, const float* __restrict__ wp,
                                                          tt_config cfg, TcSrc src, int64_t N, float* sdf_o,
                                                          float* sdf_orig_o, float* grad_o, float* normal_o,
-                                                         uint64_t* masks_o, float* __restrict__ vscratch) {
+                                                         uint64_t* masks_o, float* __restrict__ vscratch,
+                                                         float* deform_o) {
     TT_SHARED(smem);
-    using L = GeoWs<C, NORMAL>;
+    using L = GeoWs<C, NORMAL, DEFORM>;
     constexpr int SP = L::SP, CP = L::CP, U = L::U;
     const int tid = threadIdx.x, warp = tid >> 5;
     const WOff wo = woff(C);
-    btile_fill(smem + L::W1H, smem + L::W1L, 64, C, [&](int n, int k) { return __ldg(wp + wo.w1s + n * C + k); }, tid, WS_GEO_THREADS);
+    btile_fill(smem + L::W1H, smem + L::W1L, L::N1, C,
+               [&](int n, int k) { return n < 64 ? __ldg(wp + wo.w1s + n * C + k) : __ldg(wp + wo.w1d + (n - 64) * C + k); }, tid, WS_GEO_THREADS);
     btile_fill(smem + L::W2H, smem + L::W2L, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2s + n * 64 + k); }, tid, WS_GEO_THREADS);
+    if (DEFORM) {
+        btile_fill(smem + L::W2DH, smem + L::W2DL, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2d + n * 64 + k); }, tid, WS_GEO_THREADS);
+        if (tid < 192) smem[L::W3D + tid] = __ldg(wp + wo.w3d + tid);
+    }
     if (NORMAL) {
         btile_fill(smem + L::W2TH, smem + L::W2TL, 64, 64, [&](int n, int k) { return __ldg(wp + wo.w2s + k * 64 + n); }, tid, WS_GEO_THREADS);
         btile_fill(smem + L::W1TH, smem + L::W1TL, CP, 64, [&](int n, int k) { return n < C ? __ldg(wp + wo.w1s + k * C + n) : 0.f; }, tid, WS_GEO_THREADS);
@@ -373,10 +373,11 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
         u.lane_base = (uint32_t)((warp & 3) * 32) << 16;
         u.mbar = smem_u32(mmab + g); u.phase = 0; u.group = WS_GEO_NMG + g;
         const bool leader = tg == 0;
-        const BTile bW1 = btile_make(smem + L::W1H, smem + L::W1L, 64, C);
+        const BTile bW1 = btile_make(smem + L::W1H, smem + L::W1L, L::N1, C);
         const BTile bW2 = btile_make(smem + L::W2H, smem + L::W2L, 64, 64);
         const BTile bW2T = btile_make(smem + L::W2TH, smem + L::W2TL, 64, 64);
         const BTile bW1T = btile_make(smem + L::W1TH, smem + L::W1TL, CP, 64);
+        const BTile bW2D = btile_make(smem + L::W2DH, smem + L::W2DL, 64, 64);
         const float* w3 = smem + L::W3;
         float* gs = smem + L::GROUP0 + g * L::GROUP_FLOATS;
         const float* stage = gs + L::STAGE;
@@ -442,6 +443,36 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
                     masks_o[id * 4 + 2] = (uint64_t)m1[0] | ((uint64_t)m1[1] << 32);
                     masks_o[id * 4 + 3] = (uint64_t)m2[0] | ((uint64_t)m2[1] << 32);
                 }
+            }
+            if (DEFORM) {       // deformation decoder: its first layer sits in accumulator columns [192,256) since the stacked MMA
+                tc_fence_before();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float d[32];
+                    ws_ld32(u, TC_COL_D + 64 + 32 * h, d);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) d[j] = fmaxf(d[j], 0.f);
+                    ws_st32_split(u, 32 * h, d);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                group_sync(u.group);
+                if (leader) { umma_mma<3>(u, bW2D, 64, false); umma_commit(u); }
+                umma_wait(u);
+                const float* w3d = smem + L::W3D;
+                float df[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float d[32];
+                    ws_ld32(u, TC_COL_D + 32 * h, d);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = fmaxf(d[j], 0.f);
+                        df[0] = fmaf(x, w3d[32 * h + j], df[0]); df[1] = fmaf(x, w3d[64 + 32 * h + j], df[1]);
+                        df[2] = fmaf(x, w3d[128 + 32 * h + j], df[2]);
+                    }
+                }
+                if (id32 >= 0 && deform_o) { deform_o[id * 3] = df[0]; deform_o[id * 3 + 1] = df[1]; deform_o[id * 3 + 2] = df[2]; }
             }
             if (NORMAL) {       // unit-seed adjoint: a1 = m1 ⊙ (W2ᵀ a2), de = W1ᵀ a1;  d sdf / d x_a = de . V_a
                 tmem_wait_st();

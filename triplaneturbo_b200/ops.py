@@ -30,6 +30,8 @@ class PathScalars:
     near_plane: float = 0.1
     far_plane: float = 4.0
     render_step_size: float = 1.732 * 2 * 1.0 / 64
+    image_h: int = 0        # hint for tt_render_bwd: the rays are [B,image_h,image_w] images (patch-ordered sample lists)
+    image_w: int = 0
 
 
 def _lib():
@@ -54,7 +56,14 @@ def _need(t: Tensor, name: str) -> Tensor:
 
 def _cfg(C_: int, R: int, P: int, rays_per_cache: int, s: PathScalars, flags: int = 0) -> _cabi.TTConfig:
     return _cabi.TTConfig(C_, R, P, max(int(rays_per_cache), 1), s.radius, s.sdf_bias_radius, s.inv_std,
-                          s.cos_anneal_ratio, s.near_plane, s.far_plane, s.render_step_size, flags)
+                          s.cos_anneal_ratio, s.near_plane, s.far_plane, s.render_step_size, flags, int(s.image_h),
+                          int(s.image_w))
+
+
+def set_option(name: str, value: int):
+    """Experiment switches of the backward (include/triplane_b200.h tt_set_option): "scatter", "patch_lists"."""
+    L = _lib()
+    _cabi.check(L, L.tt_set_option(name.encode(), int(value)), "tt_set_option")
 
 
 def set_impl(impl: int):

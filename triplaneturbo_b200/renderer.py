@@ -8,6 +8,7 @@ Registered under the reference's names and keeping its call surface:
 One call = tt_importance_sample + tt_render_fwd (+ tt_render_bwd under autograd); nothing of size
 [rays x samples x channels] is ever materialised.
 """
+import dataclasses
 import math
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Tuple
@@ -264,7 +265,7 @@ class GenerativeSpaceSDFVolumeRenderer(BaseModule):
         n_rays = o.shape[0]
         rays_per_cache = views_per_cache * H * W
         geom = self.geometry
-        scalars = self.path_scalars()
+        scalars = dataclasses.replace(self.path_scalars(), image_h=int(H), image_w=int(W))
         weights = geom.decoder_weights()
         C_ = geom.plane_channels
 
