@@ -84,6 +84,7 @@ int tt_get_impl(void);
 /* Experiment switches of the backward (defaults are the measured-fastest settings):
  *   "scatter"     -1 auto (default), 0 plain, 1 run-length merged, 2 tile-merged hidden-gradient scatter
  *   "patch_lists"  0 (default) / 1: with tt_config.image_h/w set, tt_render_bwd visits the samples in 4x4-pixel patch order
+ *   "grid_lines"   0 (default) / 1: tt_geometry_fwd on the regular grid gathers z-lines instead of 12 taps per point
  * Initial values come from the environment (TT_SCATTER, TT_PATCH_LISTS).  Results are identical up to the summation order. */
 int tt_set_option(const char* name, int value);
 

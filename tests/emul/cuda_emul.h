@@ -189,6 +189,8 @@ inline int atomicAdd(int* addr, int v) { std::atomic_ref<int> r(*addr); return r
 inline int atomicCAS(int* addr, int expect, int desired) { return tt_emul::cas(addr, expect, desired); }
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 inline void __trap() { std::abort(); }
 using std::max;
 using std::min;

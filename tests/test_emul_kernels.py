@@ -109,14 +109,18 @@ def test_field_backward_with_deformation(em, name):
         assert rel_err(torch.from_numpy(gwd[i]), want[4 + i]) < GTOL, f"deformation {i}"
 
 
-def test_isosurface_grid_points(em):
+@pytest.mark.parametrize("res", [9, 16])        # 16: the regular-grid z-line gather of the warp-specialised kernel
+def test_isosurface_grid_points(em, res):
     fx = load_golden("geometry_c8_r16")
     w = weights_from(fx)
     cfg = em.config(8, 16, 1)
     planes = em.repack(fx["space_cache"][:1].numpy())
     wp = em.pack_weights(np_w(w), 8)
-    res = 9
-    out = em.geometry_fwd(planes, wp, cfg, None, grid_res=res, normal=False, features=False, deform=True)
+    em.set_option("grid_lines", 1 if res == 16 else 0)
+    try:
+        out = em.geometry_fwd(planes, wp, cfg, None, grid_res=res, normal=False, features=False, deform=True)
+    finally:
+        em.set_option("grid_lines", 0)
     pts = rp.isosurface_grid_points(res)[None]
     sdf, deform = rp.forward_field(pts, fx["space_cache"][:1], w, rp.PathConfig())
     assert max_abs(torch.from_numpy(out["sdf"]), sdf.reshape(-1)) < TOL

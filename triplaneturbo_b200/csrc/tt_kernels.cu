@@ -151,8 +151,9 @@ static int launch_tex_decoder(const float* planes, const float* wpack, const tt_
 }
 
 // experiment switches (tt_set_option; initial values from the environment): "scatter" = -1 auto, 0 plain, 1 run-length,
-// 2 tile-merged hidden-gradient scatter; "patch_lists" = 1: patch-ordered sample lists when the image shape is known
-static int g_opt_scatter = -2, g_opt_patch = -1;
+// 2 tile-merged hidden-gradient scatter; "patch_lists" = 1: patch-ordered sample lists when the image shape is known;
+// "grid_lines" = 1: z-line gather of the regular isosurface grid (ws_grid_segment, tt_ws.cuh)
+static int g_opt_scatter = -2, g_opt_patch = -1, g_opt_grid_lines = 0;
 static int scatter_mode() {
     if (g_opt_scatter == -2) { const char* e = getenv("TT_SCATTER"); g_opt_scatter = e ? atoi(e) : -1; }
     return g_opt_scatter;
@@ -870,6 +871,7 @@ int tt_set_option(const char* name, int value) {
     if (!name) return fail(TT_E_ARG, "tt_set_option: null name%s", "");
     if (!strcmp(name, "scatter")) { if (value < -1 || value > 2) return fail(TT_E_ARG, "tt_set_option: scatter must be -1..2%s", ""); g_opt_scatter = value; return TT_OK; }
     if (!strcmp(name, "patch_lists")) { g_opt_patch = value != 0; return TT_OK; }
+    if (!strcmp(name, "grid_lines")) { g_opt_grid_lines = value != 0; return TT_OK; }
     return fail(TT_E_ARG, "tt_set_option: unknown option '%s'", name);
 }
 int tt_set_impl(int impl) {
@@ -952,7 +954,7 @@ int tt_geometry_fwd(const float* planes, const float* wpack, const tt_config* cf
             const size_t smt = (size_t)TexSmem<kC>::TOTAL * 4;
             const bool want_n = normal || sdf_grad;
             if ((deformation ? smg_d : want_n ? smg_n : smg) <= kMaxSmem && smt <= kMaxSmem) {
-                TcSrc src{}; src.mode = points ? 0 : 3; src.points = points; src.M = M; src.grid_res = grid_res;
+                TcSrc src{}; src.mode = points ? 0 : 3; src.points = points; src.M = M; src.grid_res = grid_res; src.grid_lines = g_opt_grid_lines;
                 if (sdf || sdf_orig || want_n || deformation) {
                     if (deformation) {      // field query of the mesh paths: SDF + deformation decoders on one gather
                         const size_t smw_d = (size_t)GeoWs<kC, false, true>::TOTAL * 4;

@@ -28,7 +28,7 @@ struct TcSrc {
     const float* points; int64_t M;
     RaySrcT rs; int rays_per_cache;
     int n_imp; const float* jitter0; float near_plane, far_plane;
-    int grid_res;
+    int grid_res; int grid_lines;           // grid_lines: z-line gather for the regular grid (k_geo_ws, opt-in experiment)
     const int* index; const int* count;     // optional compaction: slot -> id, *count live slots
 };
 
@@ -43,31 +43,35 @@ __device__ __forceinline__ float grid_coord_tc(int i, int res) {
     float v = (i < res / 2) ? __fmul_rn((float)i, step) : __fsub_rn(1.f, __fmul_rn((float)(res - 1 - i), step));
     return __fadd_rn(__fmul_rn(v, 2.f), -1.f);
 }
+// (every tensor-core kernel is launched with N < 2^31 sample ids: the index arithmetic is 32-bit — a 64-bit division costs
+// ~100 instructions, and these kernels are bound by instructions per thread)
 __device__ __forceinline__ void tc_point(const TcSrc& s, int64_t id, float (&x)[3], int& prompt) {
+    const uint32_t id32 = (uint32_t)id;
     if (s.mode == 0) {
         x[0] = s.points[id * 3]; x[1] = s.points[id * 3 + 1]; x[2] = s.points[id * 3 + 2];
-        prompt = (int)(id / s.M);
+        prompt = s.M > 0x7fffffffLL ? 0 : (int)(id32 / (uint32_t)s.M);
     } else if (s.mode == 3) {
-        const int64_t v = id % s.M; const int r = s.grid_res;
-        x[0] = grid_coord_tc((int)(v / ((int64_t)r * r)), r); x[1] = grid_coord_tc((int)((v / r) % r), r);
-        x[2] = grid_coord_tc((int)(v % r), r);
-        prompt = (int)(id / s.M);
+        const uint32_t M = (uint32_t)s.M, rr = (uint32_t)s.grid_res;
+        prompt = (int)(id32 / M);
+        const uint32_t v = id32 - (uint32_t)prompt * M, xi = v / (rr * rr), rem = v - xi * rr * rr, yi = rem / rr;
+        x[0] = grid_coord_tc((int)xi, (int)rr); x[1] = grid_coord_tc((int)yi, (int)rr);
+        x[2] = grid_coord_tc((int)(rem - yi * rr), (int)rr);
     } else {
-        int64_t ray; float tm;
+        uint32_t ray; float tm;
         if (s.mode == 1) {
-            ray = id / s.rs.S; const int i = (int)(id - ray * s.rs.S);
-            const float t0 = s.rs.t_starts[ray * s.rs.t_stride + i], t1 = s.rs.t_ends[ray * s.rs.t_stride + i];
+            ray = id32 / (uint32_t)s.rs.S; const int i = (int)(id32 - ray * (uint32_t)s.rs.S);
+            const float t0 = s.rs.t_starts[(int64_t)ray * s.rs.t_stride + i], t1 = s.rs.t_ends[(int64_t)ray * s.rs.t_stride + i];
             tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
         } else {
-            ray = id / s.n_imp; const int j = (int)(id - ray * s.n_imp);
+            ray = id32 / (uint32_t)s.n_imp; const int j = (int)(id32 - ray * (uint32_t)s.n_imp);
             const bool strat = s.jitter0 != nullptr; const float b = strat ? s.jitter0[ray] : 0.f;
             const float t0 = stot_u(quantile_s(j, s.n_imp, strat, b), s.near_plane, s.far_plane);
             const float t1 = stot_u(quantile_s(j + 1, s.n_imp, strat, b), s.near_plane, s.far_plane);
             tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
         }
 #pragma unroll
-        for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(s.rs.rays_o[ray * 3 + a], __fmul_rn(s.rs.rays_d[ray * 3 + a], tm));
-        prompt = (int)(ray / s.rays_per_cache);
+        for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(s.rs.rays_o[(size_t)ray * 3 + a], __fmul_rn(s.rs.rays_d[(size_t)ray * 3 + a], tm));
+        prompt = (int)(ray / (uint32_t)s.rays_per_cache);
     }
 }
 

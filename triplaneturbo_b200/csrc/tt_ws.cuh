@@ -120,14 +120,45 @@ struct GeoWs {
     static constexpr int GROUP0 = MTAB + WS_GEO_NMG * MTAB_FLOATS;
     static constexpr int META = 0, STAGE = META + 128 * 4, GROUP_FLOATS = STAGE + 128 * SP;
     static constexpr int BARS = GROUP0 + WS_CG * GROUP_FLOATS;     // uint64: full, stage_free, mma per group
-    static constexpr int TOTAL = BARS + 2 * 3 * WS_CG + 4;
+    static constexpr int TOTAL0 = BARS + 2 * 3 * WS_CG + 4;
     static_assert(BARS % 2 == 0, "mbarriers must be 8-byte aligned");
+    // regular-grid source (isosurface grid): z-lines of a tile, see ws_grid_segment.  Tables alias MTAB (unused there).
+    static constexpr int GLMAX = 160;                              // lines per tile (all segments)
+    static constexpr bool GRID = !NORMAL && WS_GEO_NMG == 1 && (size_t)(TOTAL0 + GLMAX * C) * 4 <= 227 * 1024;
+    static constexpr int LINES = TOTAL0, TOTAL = TOTAL0 + (GRID ? GLMAX * C : 0);
+    static constexpr int G_SEG = 0, G_ZT = G_SEG + 8 * 24, G_P0 = G_ZT + 128 * 4;      // inside MTAB
+    static_assert(!GRID || G_P0 + 8 * C <= MTAB_FLOATS, "grid tables must fit in the tap tables");
     // tangent rows V_a = d enc / d x_a of a tile in the L2-resident scratch: [pt / 8][a][chunk][pt % 8][4 floats]
     // (the gather warps write 64-byte runs, the consumers read 128-byte runs)
     static constexpr int VTILE = 128 * 3 * C;                      // floats per (group, buffer)
     __host__ __device__ static constexpr int vidx(int pt, int a, int ch) { return ((((pt >> 3) * 3 + a) * U + ch) * 8 + (pt & 7)) * 4; }
 };
 __host__ __device__ constexpr size_t ws_vscratch_floats(int n_cta, int C) { return (size_t)n_cta * WS_CG * 2 * 128 * 3 * C; }
+
+// Regular-grid source (src.mode == 3, the 512^3 isosurface grid of the mesh export): a tile is `128 / SL` SEGMENTS of SL
+// consecutive grid points along z with (x, y) fixed, so
+//   * plane 0 (x, y) contributes ONE blended vector per segment,
+//   * plane 1 (x, z) and plane 2 (z, y) are bilinear in z over LINES that depend on the texel row / column z_i only:
+//       line(z_i) = wx0 T1[z_i][x0] + wx1 T1[z_i][x0+1] + wy0 T2[y0][z_i] + wy1 T2[y0+1][z_i],
+//     and a point is  e = P0 + wz0 line(z0) + wz1 line(z0 + 1).
+// Per tile the gather warps load 4 + 4 x (lines) texels instead of 12 x 128 (config 5: 66 lines, 268 texels: 5.7x fewer
+// loads and blend instructions).  Returns SL (0: not applicable -> generic gather).  Same formula on host and device.
+__host__ __device__ inline int ws_grid_segment(int rr, int R, int lmax) {
+    if (rr < 16) return 0;
+    const int SL = rr < 128 ? rr : 128;
+    if (128 % SL != 0 || rr % SL != 0) return 0;
+    const int span = (int)(((long long)(SL - 1) * R) / (rr - 1)) + 3;      // texel rows a segment can touch (+ slack)
+    return (128 / SL) * span <= lmax ? SL : 0;
+}
+
+// lower texel index and the two weights of a coordinate along one plane axis: the arithmetic of make_taps (tt_device.cuh)
+__device__ __forceinline__ void ws_axis_tap(float g, int R, int& i0, float (&w)[2]) {
+    const float fR = (float)R;
+    const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), fR), 1.f), 0.5f);
+    const float x0f = floorf(ix);
+    w[0] = __fsub_rn(__fadd_rn(x0f, 1.f), ix); w[1] = __fsub_rn(ix, x0f);
+    i0 = (int)fminf(fmaxf(x0f, -2.f), fR + 2.f);
+}
 
 // Sample of a gather job, prefetched one job ahead as RAW loaded words: the arithmetic that turns them into a position
 // runs one job later, so the global-load latency (sample id -> interval edges / ray) hides behind the previous gather.
@@ -165,12 +196,14 @@ __device__ __forceinline__ void ws_point_from_raw(const TcSrc& s, const WsRaw& r
     if (r.id < 0) return;
     if (s.mode == 0) {
         x[0] = r.v[0]; x[1] = r.v[1]; x[2] = r.v[2];
-        prompt = (int)((int64_t)r.id / s.M);
+        prompt = s.M > 0x7fffffffLL ? 0 : (int)((uint32_t)r.id / (uint32_t)s.M);
     } else if (s.mode == 3) {
-        const int64_t v = (int64_t)r.id % s.M; const int rr = s.grid_res;
-        x[0] = grid_coord_tc((int)(v / ((int64_t)rr * rr)), rr); x[1] = grid_coord_tc((int)((v / rr) % rr), rr);
-        x[2] = grid_coord_tc((int)(v % rr), rr);
-        prompt = (int)((int64_t)r.id / s.M);
+        // (sample ids are 32-bit here and M = rr^3 <= N < 2^31: 32-bit divisions, a 64-bit one costs ~100 instructions)
+        const uint32_t M = (uint32_t)s.M, rr = (uint32_t)s.grid_res;
+        prompt = (int)((uint32_t)r.id / M);
+        const uint32_t v = (uint32_t)r.id - (uint32_t)prompt * M, xi = v / (rr * rr), rem = v - xi * rr * rr, yi = rem / rr;
+        x[0] = grid_coord_tc((int)xi, (int)rr); x[1] = grid_coord_tc((int)yi, (int)rr);
+        x[2] = grid_coord_tc((int)(rem - yi * rr), (int)rr);
     } else {
         int ray; float tm;
         if (s.mode == 1) {
@@ -230,6 +263,7 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
     const int64_t n_live = src.count ? (int64_t)*src.count : N;
     const int64_t n_tiles = (n_live + TC_GROUP - 1) / TC_GROUP;
     const int64_t tile_stride = (int64_t)gridDim.x * WS_CG;
+    const int grid_sl = (L::GRID && src.mode == 3 && src.grid_lines && !src.index) ? ws_grid_segment(src.grid_res, cfg.R, L::GLMAX) : 0;   // regular-grid gather
     float* vcta = NORMAL ? vscratch + (size_t)blockIdx.x * WS_CG * 2 * L::VTILE : nullptr;
     // gather jobs.  One gather warpgroup: job j serves consumer group j & 1 with its tile number j >> 1.  Two: warpgroup m
     // serves consumer group m, job j = its tile number j.
@@ -261,6 +295,119 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
             const bool valid = cur.id >= 0;
             float cx_[3]; int cprompt;
             ws_point_from_raw(src, cur, cx_, cprompt);
+            if (L::GRID && grid_sl > 0) {
+                // ================================================================ regular grid: z-lines (ws_grid_segment)
+                const int SL = grid_sl, NSEG = 128 / SL, LSEG = L::GLMAX / NSEG;
+                int* seg = reinterpret_cast<int*>(tab + L::G_SEG);
+                float* zt = tab + L::G_ZT; float* p0 = tab + L::G_P0; float* lines = smem + L::LINES;
+                int x0, y0, z0; float wx[2], wy[2], wz[2];
+                ws_axis_tap(rescale1(cx_[0], cfg.radius), cfg.R, x0, wx);
+                ws_axis_tap(rescale1(cx_[1], cfg.radius), cfg.R, y0, wy);
+                ws_axis_tap(rescale1(cx_[2], cfg.radius), cfg.R, z0, wz);
+                group_sync(mgrp);                   // every gather thread is done with the previous job's tables
+                const int sg = mt / SL, sl = mt - sg * SL;
+                if (sl == 0) {
+                    int* q = seg + sg * 24;
+                    const bool xv[2] = {x0 >= 0 && x0 < cfg.R, x0 + 1 >= 0 && x0 + 1 < cfg.R};
+                    const bool yv[2] = {y0 >= 0 && y0 < cfg.R, y0 + 1 >= 0 && y0 + 1 < cfg.R};
+                    q[0] = valid ? 1 : 0; q[1] = cprompt; q[2] = z0;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {        // plane 0 (x, y): nw, ne, sw, se as make_taps
+                        const bool in = xv[t & 1] && yv[t >> 1];
+                        q[4 + t] = in ? (y0 + (t >> 1)) * cfg.R + x0 + (t & 1) : -1;
+                        q[8 + t] = (int)__float_as_uint(in ? __fmul_rn(wx[t & 1], wy[t >> 1]) : 0.f);
+                    }
+                    q[12] = x0; q[13] = y0;              // plane 1 (x, z): columns x0, x0 + 1 ; plane 2 (z, y): rows y0, y0 + 1
+                    q[14] = (int)__float_as_uint(xv[0] ? wx[0] : 0.f); q[15] = (int)__float_as_uint(xv[1] ? wx[1] : 0.f);
+                    q[16] = (int)__float_as_uint(yv[0] ? wy[0] : 0.f); q[17] = (int)__float_as_uint(yv[1] ? wy[1] : 0.f);
+                }
+                if (sl == SL - 1) seg[sg * 24 + 3] = z0 + 1;          // last line of the segment
+                group_sync(mgrp);
+                {   // this point's z taps relative to the segment's first line
+                    const int zlo = seg[sg * 24 + 2];
+                    *reinterpret_cast<float4*>(zt + mt * 4) = make_float4(__int_as_float(z0 - zlo), wz[0], wz[1], 0.f);
+                }
+                // ---- build: P0 per segment and the z-lines (both planes summed), item = (segment, line, 16-byte chunk).
+                // All loads of the tile are issued before the first one is used (a thread holds up to 4 + 4 GB texel
+                // chunks in registers): the phase costs ONE memory latency instead of one per batch.
+                int nl = 0;                         // lines of the longest segment
+                for (int s_ = 0; s_ < NSEG; ++s_) { const int n_ = seg[s_ * 24 + 3] - seg[s_ * 24 + 2] + 1; nl = n_ > nl ? n_ : nl; }
+                nl = nl < LSEG ? nl : LSEG;
+                const int n_line_items = NSEG * nl * U;
+                constexpr int GB = 5;
+                float4 pv[4]; float pw[4];
+                const bool p0_item = mt < NSEG * U;
+                {
+                    const int s_ = p0_item ? mt / U : 0, ch = p0_item ? mt - s_ * U : 0;
+                    const int* q = seg + s_ * 24;
+                    const float* pb = planes + (size_t)q[1] * 6 * ps + ch * 4;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        pw[t] = (p0_item && q[0] && q[4 + t] >= 0) ? __uint_as_float((uint32_t)q[8 + t]) : 0.f;
+                        pv[t] = pw[t] != 0.f ? ldg4(pb + (size_t)q[4 + t] * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll 1
+                for (int it0 = mt; it0 < n_line_items; it0 += GB * WS_M) {
+                    float4 v[GB][4]; float w[GB][4]; int li[GB];
+#pragma unroll
+                    for (int b = 0; b < GB; ++b) {
+                        const int it = it0 + b * WS_M;
+                        const bool ok = it < n_line_items;
+                        const int itc = ok ? it : it0;
+                        const int ch = itc % U, ln = itc / U, s_ = NSEG == 1 ? 0 : (int)((uint32_t)ln / (uint32_t)nl), l = ln - s_ * nl;
+                        li[b] = ok ? (s_ * LSEG + l) * C + ch * 4 : -1;
+                        const int* q = seg + s_ * 24;
+                        const int zi = q[2] + l;
+                        const bool in = ok && q[0] && zi >= 0 && zi < cfg.R && zi <= q[3];
+                        const int x0 = q[12], y0 = q[13];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { w[b][t] = in ? __uint_as_float((uint32_t)q[14 + t]) : 0.f; v[b][t] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                        const float* pb = planes + (size_t)q[1] * 6 * ps + ch * 4;
+                        if (w[b][0] != 0.f) v[b][0] = ldg4(pb + ps + ((size_t)zi * cfg.R + x0) * C);
+                        if (w[b][1] != 0.f) v[b][1] = ldg4(pb + ps + ((size_t)zi * cfg.R + x0 + 1) * C);
+                        if (w[b][2] != 0.f) v[b][2] = ldg4(pb + 2 * ps + ((size_t)y0 * cfg.R + zi) * C);
+                        if (w[b][3] != 0.f) v[b][3] = ldg4(pb + 2 * ps + ((size_t)(y0 + 1) * cfg.R + zi) * C);
+                    }
+#pragma unroll
+                    for (int b = 0; b < GB; ++b) {
+                        if (li[b] < 0) continue;
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { a.x = fmaf(w[b][t], v[b][t].x, a.x); a.y = fmaf(w[b][t], v[b][t].y, a.y); a.z = fmaf(w[b][t], v[b][t].z, a.z); a.w = fmaf(w[b][t], v[b][t].w, a.w); }
+                        *reinterpret_cast<float4*>(lines + li[b]) = a;
+                    }
+                }
+                if (p0_item) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) { a.x = fmaf(pw[t], pv[t].x, a.x); a.y = fmaf(pw[t], pv[t].y, a.y); a.z = fmaf(pw[t], pv[t].z, a.z); a.w = fmaf(pw[t], pv[t].w, a.w); }
+                    *reinterpret_cast<float4*>(p0 + mt * 4) = a;          // = p0[s_ * C + ch * 4]
+                }
+                WS_ACC(1, tm, prof_m);
+                mbar_wait_parity(smem_u32(sfree + g), par ^ 1u);        // the group has taken its previous tile out of the stage
+                WS_ACC(0, tm, prof_m);
+                *reinterpret_cast<float4*>(gs + L::META + mt * 4) =
+                    make_float4(__uint_as_float((uint32_t)cur.id), cx_[0], cx_[1], cx_[2]);
+                group_sync(mgrp);
+                // ---- blend: item = (point, 16-byte chunk)
+                float* stage = gs + L::STAGE;
+#pragma unroll 2
+                for (int it = mt; it < 128 * U; it += WS_M) {
+                    const int pt = it / U, ch = it - pt * U, s_ = pt / SL;
+                    const float4 z4 = *reinterpret_cast<const float4*>(zt + pt * 4);
+                    const int l0 = __float_as_int(z4.x);
+                    const float* ln = lines + (s_ * LSEG + l0) * C + ch * 4;
+                    float4 e = *reinterpret_cast<const float4*>(p0 + s_ * C + ch * 4);
+                    if (l0 >= 0) { const float4 a = *reinterpret_cast<const float4*>(ln); e.x = fmaf(z4.y, a.x, e.x); e.y = fmaf(z4.y, a.y, e.y); e.z = fmaf(z4.y, a.z, e.z); e.w = fmaf(z4.y, a.w, e.w); }
+                    if (l0 + 1 >= 0 && l0 + 1 < LSEG) { const float4 a = *reinterpret_cast<const float4*>(ln + C); e.x = fmaf(z4.z, a.x, e.x); e.y = fmaf(z4.z, a.y, e.y); e.z = fmaf(z4.z, a.z, e.z); e.w = fmaf(z4.z, a.w, e.w); }
+                    *reinterpret_cast<float4*>(stage + pt * SP + ch * 4) = e;
+                }
+                mbar_arrive(smem_u32(full + g));
+                WS_ACC(2, tm, prof_m);
+                cur = nxt;
+                continue;
+            }
             Taps tp[3];
             {
                 float p[3];
