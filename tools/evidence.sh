@@ -6,12 +6,12 @@ K='geometry_plugin_matches_reference or forward_field_grid or renderer_training_
 if [ "$part" = sanitizer ] || [ "$part" = all ]; then
   for tool in racecheck synccheck memcheck; do
     for fam in tcgen05-ws tcgen05-r1; do
-      timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -q -x \
-          -k "$fam and ($K)" > gpurun_out/r02_sanitizer_${tool}_${fam}.log 2>&1
+      timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_gpu_parity.py tests/test_gpu_options.py -m gpu -q -x \
+          -k "$fam and ($K) or tiny and $fam or grid_line_gather and 8-16-16" > gpurun_out/r02_sanitizer_${tool}_${fam}.log 2>&1
       echo "$tool $fam rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/r02_sanitizer_${tool}_${fam}.log | tr '\n' ' ')"
     done
   done
-  # the round-1 kernels built without the memory-phase lock
+  # the round-1 kernels built without the memory-phase lock (TT_LIBNAME=libtriplane_b200_nolock.so bash triplaneturbo_b200/csrc/build.sh -DTT_MEMLOCK=0)
   TT_B200_LIB=$PWD/triplaneturbo_b200/lib/libtriplane_b200_nolock.so timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 \
       python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "tcgen05-r1 and ($K)" > gpurun_out/r02_sanitizer_racecheck_tcgen05-r1_nolock.log 2>&1
   echo "racecheck r1 nolock rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/r02_sanitizer_racecheck_tcgen05-r1_nolock.log | tr '\n' ' ')"
