@@ -1347,7 +1347,8 @@ static int sample_args(const char* who, const float* planes, int N, int K, int C
     if (!aligned16(planes)) return fail(TT_E_ALIGN, "%s: planes must be 16-byte aligned", who);
     int seg = 1;
     while (seg < (C >> 2) && seg < 32) seg <<= 1;
-    *a = SampleArgs{planes, grid, N, K, C, H, W, M, concat ? 1 : 0, seg};
+    const int lanes = seg > (C >> 2) ? seg : (C >> 2);
+    *a = SampleArgs{planes, grid, N, K, C, H, W, M, concat ? 1 : 0, seg, ((int64_t)N * M * lanes + 256 < 0xffffffffLL && M < 0x7fffffffLL) ? 1 : 0};
     return TT_OK;
 }
 static unsigned sample_grid_dim(const SampleArgs& a) { return (unsigned)(((int64_t)a.N * a.M * a.seg + 255) / 256); }
@@ -1359,11 +1360,12 @@ int tt_sample_planes_fwd(const float* planes, int N, int K, int C, int H, int W,
     if (int e = sample_args("tt_sample_planes_fwd", planes, N, K, C, H, W, grid, M, concat, &a)) return e;
     if (!out || !aligned16(out)) return fail(TT_E_ARG, "tt_sample_planes_fwd: out NULL or misaligned%s", "");
     if ((int64_t)N * M == 0) return TT_OK;
+    const bool i32 = a.i32 != 0;       // item index fits 32 bits: 32-bit divisions
     switch (K) {
-        case 1: TT_LAUNCH(k_sample_fwd<1>, sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
-        case 2: TT_LAUNCH(k_sample_fwd<2>, sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
-        case 3: TT_LAUNCH(k_sample_fwd<3>, sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
-        default: TT_LAUNCH(k_sample_fwd<4>, sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
+        case 1: if (i32) TT_LAUNCH((k_sample_fwd<1, true>), sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); else TT_LAUNCH((k_sample_fwd<1, false>), sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
+        case 2: if (i32) TT_LAUNCH((k_sample_fwd<2, true>), sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); else TT_LAUNCH((k_sample_fwd<2, false>), sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
+        case 3: if (i32) TT_LAUNCH((k_sample_fwd<3, true>), sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); else TT_LAUNCH((k_sample_fwd<3, false>), sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
+        default: if (i32) TT_LAUNCH((k_sample_fwd<4, true>), sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); else TT_LAUNCH((k_sample_fwd<4, false>), sample_grid_flat(a), 256, 0, (cudaStream_t)stream, a, out); break;
     }
     return check_launch("tt_sample_planes_fwd");
 }

@@ -52,51 +52,78 @@ __device__ __forceinline__ float seg_sum(float v, int seg) {
 struct SampleArgs {
     const float* planes; const float* grid;
     int N, K, C, H, W; int64_t M; int concat; int seg;
+    int i32;                     // N * M * max(seg, C/4) + 256 < 2^32: thread and point indices split with 32-bit divisions
 };
+// thread -> (point, lane of the point's segment), point -> (sample set, point of the set)
+__device__ __forceinline__ void sample_split(const SampleArgs& a, int64_t& pt0, int& l) {
+    if (a.i32) { const uint32_t t = blockIdx.x * 256u + threadIdx.x, p = t / (uint32_t)a.seg; pt0 = p; l = (int)(t - p * (uint32_t)a.seg); }
+    else { const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; pt0 = t / a.seg; l = (int)(t % a.seg); }
+}
+__device__ __forceinline__ void sample_set(const SampleArgs& a, int64_t pt, int64_t& n, int64_t& m) {
+    if (a.i32) { const uint32_t n32 = (uint32_t)pt / (uint32_t)a.M; n = n32; m = (uint32_t)pt - n32 * (uint32_t)a.M; }
+    else { n = pt / a.M; m = pt - n * a.M; }
+}
 
-template <int K>
+// I32: the item index (point, chunk) fits 32 bits (the usual case): 32-bit divisions.  All 4K taps of an item are loaded
+// unconditionally (an out-of-bounds tap reads texel 0 with weight 0) so that they are in flight together, and the output
+// row is written with streaming stores: it is never read again and must not evict the planes from L2.
+template <int K, bool I32>
 __global__ void __launch_bounds__(256) k_sample_fwd(SampleArgs a, float* __restrict__ out) {
-    // the forward needs no reduction over the lanes of a point: items (point, chunk) are simply flattened over the threads
     const int U = a.C >> 2, OS = a.concat ? K * a.C : a.C;
-    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int64_t pt = t / U; const int ch = (int)(t - pt * U);
-    if (pt >= (int64_t)a.N * a.M) return;
-    const int64_t n = pt / a.M, m = pt - n * a.M;
+    int64_t pt, n, m; int ch;
+    if (I32) {
+        const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+        const uint32_t p32 = t / (uint32_t)U; ch = (int)(t - p32 * (uint32_t)U);
+        if ((int64_t)p32 >= (int64_t)a.N * a.M) return;
+        const uint32_t n32 = p32 / (uint32_t)a.M;
+        pt = p32; n = n32; m = p32 - n32 * (uint32_t)a.M;
+    } else {
+        const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+        pt = t / U; ch = (int)(t - pt * U);
+        if (pt >= (int64_t)a.N * a.M) return;
+        n = pt / a.M; m = pt - n * a.M;
+    }
     const size_t ps = (size_t)a.H * a.W * a.C;
-    TapsHW tp[K];
+    float4 v[K][4]; float w[K][4]; unsigned in_mask = 0u;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const float* g = a.grid + (((size_t)n * K + k) * a.M + m) * 2;
-        tp[k] = make_taps_hw(g[0], g[1], a.H, a.W);
+        const float2 g = __ldg(reinterpret_cast<const float2*>(a.grid + (((size_t)n * K + k) * a.M + m) * 2));
+        const TapsHW tp = make_taps_hw(g.x, g.y, a.H, a.W);
+        const float* base = a.planes + ((size_t)n * K + k) * ps + ch * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool in = tp.o[q] >= 0;
+            in_mask |= in ? (1u << (k * 4 + q)) : 0u;
+            w[k][q] = tp.w[q];
+            v[k][q] = ldg4(base + (size_t)(in ? tp.o[q] : 0) * a.C);
+        }
     }
     float* orow = out + (size_t)pt * OS;
-    {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float* base = a.planes + ((size_t)n * K + k) * ps + ch * 4;
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < K; ++k) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (tp[k].o[q] >= 0) {
-                    const float4 v = ldg4(base + (size_t)tp[k].o[q] * a.C); const float w = tp[k].w[q];
-                    s.x = fmaf(w, v.x, s.x); s.y = fmaf(w, v.y, s.y); s.z = fmaf(w, v.z, s.z); s.w = fmaf(w, v.w, s.w);
-                }
-            if (a.concat) *reinterpret_cast<float4*>(orow + k * a.C + ch * 4) = s;
-            else { acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w; }
-        }
-        if (!a.concat) *reinterpret_cast<float4*>(orow + ch * 4) = acc;
+        for (int q = 0; q < 4; ++q)
+            if ((in_mask >> (k * 4 + q)) & 1u) {      // out-of-bounds taps were loaded from texel 0 and are dropped here
+                s.x = fmaf(w[k][q], v[k][q].x, s.x); s.y = fmaf(w[k][q], v[k][q].y, s.y);
+                s.z = fmaf(w[k][q], v[k][q].z, s.z); s.w = fmaf(w[k][q], v[k][q].w, s.w);
+            }
+        if (a.concat) __stcs(reinterpret_cast<float4*>(orow + k * a.C + ch * 4), s);
+        else { acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w; }
     }
+    if (!a.concat) __stcs(reinterpret_cast<float4*>(orow + ch * 4), acc);
 }
 
 // d/d planes (accumulated, nullable) and d/d grid (written, nullable) for the upstream gradient g_out [N][M][OS]
 __global__ void __launch_bounds__(256) k_sample_bwd(SampleArgs a, const float* __restrict__ g_out,
                                                    float* __restrict__ g_planes, float* __restrict__ g_grid) {
-    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int64_t pt0 = t / a.seg; const int l = (int)(t % a.seg);
+    int64_t pt0; int l;
+    sample_split(a, pt0, l);
     const bool act = pt0 < (int64_t)a.N * a.M;
     const int64_t pt = act ? pt0 : 0;
-    const int64_t n = pt / a.M, m = pt - n * a.M;
+    int64_t n, m;
+    sample_set(a, pt, n, m);
     const int U = a.C >> 2, OS = a.concat ? a.K * a.C : a.C;
     const size_t ps = (size_t)a.H * a.W * a.C;
     for (int k = 0; k < a.K; ++k) {
@@ -137,11 +164,12 @@ __global__ void __launch_bounds__(256) k_sample_bwdbwd(SampleArgs a, const float
                                                       const float* __restrict__ gg_planes, const float* __restrict__ gg_grid,
                                                       float* __restrict__ gg_out, float* __restrict__ g_planes,
                                                       float* __restrict__ g_grid) {
-    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int64_t pt0 = t / a.seg; const int l = (int)(t % a.seg);
+    int64_t pt0; int l;
+    sample_split(a, pt0, l);
     const bool act = pt0 < (int64_t)a.N * a.M;
     const int64_t pt = act ? pt0 : 0;
-    const int64_t n = pt / a.M, m = pt - n * a.M;
+    int64_t n, m;
+    sample_set(a, pt, n, m);
     const int U = a.C >> 2, OS = a.concat ? K * a.C : a.C;
     const size_t ps = (size_t)a.H * a.W * a.C;
     const float sx = 0.5f * (float)a.W, sy = 0.5f * (float)a.H;
