@@ -9,15 +9,15 @@ gather-based op (twice differentiable through autograd), or - when oracle/_ref/g
 reference's own sampler stack: ATen grid_sample forward, aten::grid_sampler_2d_backward, and the reference's grad2_2d
 CUDA kernel for the backward of the backward (the structure of extern/grid_sample_gradfix/cuda_gridsample.py:22-79).
 One fwd+bwd step on a bounded sample of config 2 (1 prompt x 1 view x HxH rays); prints one JSON line.
-    python tools/bench_reference_gpu.py [H=96] [manual|ref]"""
+    python tests/tools/bench_reference_gpu.py [H=96] [manual|ref]"""
 import json, os, sys, time
 import torch
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import reference_path as rp
 from triplaneturbo_b200.synthetic import camera_rays, random_decoder, random_triplanes
 
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 96
-REF_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "gridsample_grad2_ref.so")
+REF_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "oracle", "_ref", "gridsample_grad2_ref.so")
 mode = sys.argv[2] if len(sys.argv) > 2 else ("ref" if os.path.exists(REF_SO) else "manual")
 if mode == "ref":
     import importlib.util

@@ -3,7 +3,7 @@
 sample positions (oracle sampler on a 32 x 32 pixel window of a 512^2 view).  CPU only (~1 min).  DESIGN 3.5 item 10."""
 import sys, torch, numpy as np
 import os
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from triplaneturbo_b200.synthetic import camera_rays, random_triplanes, random_decoder
 from oracle import reference_path as rp
 torch.manual_seed(0)
