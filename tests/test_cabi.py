@@ -27,6 +27,13 @@ def lib():
 
 def test_header_and_binding_agree():
     assert header_functions() == sorted(_cabi.SIGNATURES)
+    # tt_config travels by pointer through the ABI: 12 scalars + the optional image shape, 4 bytes each (the .cu asserts 56 too)
+    assert C.sizeof(_cabi.TTConfig) == 56
+    src = open(os.path.join(ROOT, "include", "triplane_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", src[src.index("/* Scalars of the path"):src.index("} tt_config;")], flags=re.S)
+    fields = re.findall(r"\b(?:int32_t|float)\s+([a-z_A-Z, ]+);", body)
+    names = [n.strip() for f in fields for n in f.split(",")]
+    assert names == [n for n, _ in _cabi.TTConfig._fields_], names
 
 
 def test_library_exports_every_declared_symbol(lib):

@@ -7,6 +7,7 @@
 #include "tt_rays.cuh"
 #include "tt_sampler.cuh"
 
+static_assert(sizeof(tt_config) == 56, "tt_config is part of the C ABI: 14 x 4 bytes (INTEGRATION.md section 2)");
 #include <atomic>
 #include <cstdlib>
 #include <cstdio>
