@@ -119,8 +119,14 @@ struct GeoWs {
     // per consumer group: meta (id, x) and the blended encodings of its next tile
     static constexpr int GROUP0 = MTAB + WS_GEO_NMG * MTAB_FLOATS;
     static constexpr int META = 0, STAGE = META + 128 * 4, GROUP_FLOATS = STAGE + 128 * SP;
-    static constexpr int BARS = GROUP0 + WS_CG * GROUP_FLOATS;     // uint64: full, stage_free, mma per group
-    static constexpr int TOTAL0 = BARS + 2 * 3 * WS_CG + 4;
+    static constexpr int BARS = GROUP0 + WS_CG * GROUP_FLOATS;     // uint64: full, stage_free, mma, tables_ready per group
+    // CTAB (kernels without the normal): the CONSUMER groups compute the tap tables of their next tile (thread = point, in
+    // the shadow of their MMA round trips) and hand them to the gather warps through `tables_ready`; the gather warps only
+    // gather.  Group 0's tables live in MTAB, group 1's in CTAB1.
+    static constexpr bool CTAB = !NORMAL && WS_GEO_NMG == 1;
+    static constexpr int CTAB1 = BARS + 2 * 4 * WS_CG + 4;
+    static constexpr int TOTAL0 = CTAB1 + (CTAB ? MTAB_FLOATS : 0);
+    static_assert(CTAB1 % 4 == 0, "table buffers are read as 16-byte vectors");
     static_assert(BARS % 2 == 0, "mbarriers must be 8-byte aligned");
     // regular-grid source (isosurface grid): z-lines of a tile, see ws_grid_segment.  Tables alias MTAB (unused there).
     static constexpr int GLMAX = 160;                              // lines per tile (all segments)
@@ -248,10 +254,10 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
     }
     if (tid < 64) smem[L::W3 + tid] = __ldg(wp + wo.w3s + tid);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BARS);
-    uint64_t* full = bars; uint64_t* sfree = bars + WS_CG; uint64_t* mmab = bars + 2 * WS_CG;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WS_CG);
+    uint64_t* full = bars; uint64_t* sfree = bars + WS_CG; uint64_t* mmab = bars + 2 * WS_CG; uint64_t* tready = bars + 3 * WS_CG;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * WS_CG);
     if (tid == 0) {
-        for (int g = 0; g < WS_CG; ++g) { mbar_init_n(full + g, WS_M); mbar_init_n(sfree + g, TC_GROUP); mbar_init_n(mmab + g, 1); }
+        for (int g = 0; g < WS_CG; ++g) { mbar_init_n(full + g, WS_M); mbar_init_n(sfree + g, TC_GROUP); mbar_init_n(mmab + g, 1); mbar_init_n(tready + g, TC_GROUP); }
         mbar_init_fence();
     }
     if (warp == 0) tmem_alloc_warp(tmem_slot, 512);
@@ -264,6 +270,8 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
     const int64_t n_tiles = (n_live + TC_GROUP - 1) / TC_GROUP;
     const int64_t tile_stride = (int64_t)gridDim.x * WS_CG;
     const int grid_sl = (L::GRID && src.mode == 3 && src.grid_lines && !src.index) ? ws_grid_segment(src.grid_res, cfg.R, L::GLMAX) : 0;   // regular-grid gather
+    const bool ctab = L::CTAB && grid_sl == 0;          // tap tables by the consumer groups
+    auto ctab_of = [&](int g) { return smem + (g == 0 ? L::MTAB : L::CTAB1); };
     float* vcta = NORMAL ? vscratch + (size_t)blockIdx.x * WS_CG * 2 * L::VTILE : nullptr;
     // gather jobs.  One gather warpgroup: job j serves consumer group j & 1 with its tile number j >> 1.  Two: warpgroup m
     // serves consumer group m, job j = its tile number j.
@@ -284,6 +292,63 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
         WS_T0(tm);
         // software pipeline over jobs: sample ids two jobs ahead, sample positions one job ahead (both are dependent
         // global loads whose latency would otherwise be exposed once per tile)
+        if (ctab) {
+            // the consumer group publishes the tables of its tile (tready), the gather warps blend it into the group's stage
+            for (int64_t j = 0; job_tile(j) < n_tiles; ++j) {
+                const int g = job_group(j);
+                const uint32_t par = (uint32_t)(job_num(j) & 1);
+                float* gs = smem + L::GROUP0 + g * L::GROUP_FLOATS;
+                const float* ct = ctab_of(g);
+                const int* t_o = reinterpret_cast<const int*>(ct + L::TAP_O);
+                const float* t_w = ct + L::TAP_W;
+                const uint32_t* t_p = reinterpret_cast<const uint32_t*>(ct + L::PBASE);
+                mbar_wait_parity(smem_u32(tready + g), par);
+                WS_ACC(1, tm, prof_m);
+                mbar_wait_parity(smem_u32(sfree + g), par ^ 1u);        // the group has taken its previous tile out of the stage
+                WS_ACC(0, tm, prof_m);
+                float* stage = gs + L::STAGE;
+                constexpr int JB = WS_GATHER_JB, ITEMS = 128 * U;
+#pragma unroll 1
+                for (int i0 = mt; i0 < ITEMS; i0 += JB * WS_M) {
+                    float4 v[JB][12];
+                    int pt[JB], ch[JB];
+#pragma unroll
+                    for (int b = 0; b < JB; ++b) {
+                        const int item = i0 + b * WS_M < ITEMS ? i0 + b * WS_M : ITEMS - 1;      // tail: repeat the last item (not stored)
+                        pt[b] = item / U; ch[b] = item - pt[b] * U;
+                        const float* base = planes + (size_t)t_p[pt[b]] * 6 * ps + ch[b] * 4;
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk) {
+                            const int4 o4 = *reinterpret_cast<const int4*>(t_o + pt[b] * 12 + kk * 4);
+                            const float* pb = base + (size_t)kk * ps;
+                            v[b][kk * 4 + 0] = ldg4(pb + (size_t)o4.x * C); v[b][kk * 4 + 1] = ldg4(pb + (size_t)o4.y * C);
+                            v[b][kk * 4 + 2] = ldg4(pb + (size_t)o4.z * C); v[b][kk * 4 + 3] = ldg4(pb + (size_t)o4.w * C);
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < JB; ++b) {
+                        if (i0 + b * WS_M >= ITEMS) continue;
+                        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(t_w + pt[b] * 12 + kk * 4);
+                            const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+                            float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float4 q = v[b][kk * 4 + t];
+                                sacc.x = fmaf(ww[t], q.x, sacc.x); sacc.y = fmaf(ww[t], q.y, sacc.y);
+                                sacc.z = fmaf(ww[t], q.z, sacc.z); sacc.w = fmaf(ww[t], q.w, sacc.w);
+                            }
+                            e.x += sacc.x; e.y += sacc.y; e.z += sacc.z; e.w += sacc.w;
+                        }
+                        *reinterpret_cast<float4*>(stage + pt[b] * SP + ch[b] * 4) = e;
+                    }
+                }
+                mbar_arrive(smem_u32(full + g));
+                WS_ACC(2, tm, prof_m);
+            }
+        } else {
         WsRaw cur = ws_load_raw(src, ws_load_id(src, job_tile(0), mt, n_live, n_tiles));
         int id_next = ws_load_id(src, job_tile(1), mt, n_live, n_tiles);
         for (int64_t j = 0; job_tile(j) < n_tiles; ++j) {
@@ -511,6 +576,7 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
             WS_ACC(2, tm, prof_m);
             cur = nxt;
         }
+        }
     } else {
         // ============================================================================ consumer groups
         ws_reg_dec<WS_REG_C>();
@@ -531,13 +597,47 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
         int64_t k = 0;
         const bool prof_c = blockIdx.x == 0 && g == 0 && tg == 0; (void)prof_c;
         WS_T0(tc);
-        for (int64_t tile = (int64_t)blockIdx.x * WS_CG + g; tile < n_tiles; tile += tile_stride, ++k) {
+        // CTAB: this thread's point of the group's NEXT tile — id and raw words prefetched one tile further, the tap tables
+        // written to the group's buffer once the gather of the current tile is complete (full), then `tready`.
+        const int64_t tile0 = (int64_t)blockIdx.x * WS_CG + g;
+        float4 mv_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        WsRaw raw_next; raw_next.id = -1; int id_after = -1;
+        auto publish_tables = [&](const WsRaw& r) {
+            float x[3]; int prompt;
+            ws_point_from_raw(src, r, x, prompt);
+            const bool valid = r.id >= 0;
+            float p[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
+            float* ct = ctab_of(g);
+            int* t_o = reinterpret_cast<int*>(ct + L::TAP_O); float* t_w = ct + L::TAP_W;
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk) {
+                const Taps tp = make_taps(p[plane_ax(kk)], p[plane_ay(kk)], cfg.R);
+                int4 o4; float4 w4;
+                const bool i0 = valid && tp.o[0] >= 0, i1 = valid && tp.o[1] >= 0, i2 = valid && tp.o[2] >= 0, i3 = valid && tp.o[3] >= 0;
+                o4.x = i0 ? tp.o[0] : 0; o4.y = i1 ? tp.o[1] : 0; o4.z = i2 ? tp.o[2] : 0; o4.w = i3 ? tp.o[3] : 0;
+                w4.x = i0 ? tp.w[0] : 0.f; w4.y = i1 ? tp.w[1] : 0.f; w4.z = i2 ? tp.w[2] : 0.f; w4.w = i3 ? tp.w[3] : 0.f;
+                *reinterpret_cast<int4*>(t_o + tg * 12 + kk * 4) = o4;
+                *reinterpret_cast<float4*>(t_w + tg * 12 + kk * 4) = w4;
+            }
+            reinterpret_cast<uint32_t*>(ct + L::PBASE)[tg] = (uint32_t)prompt;
+            mbar_arrive(smem_u32(tready + g));
+            return make_float4(__uint_as_float((uint32_t)r.id), x[0], x[1], x[2]);
+        };
+        if (ctab && tile0 < n_tiles) {
+            const WsRaw r0 = ws_load_raw(src, ws_load_id(src, tile0, tg, n_live, n_tiles));
+            raw_next = ws_load_raw(src, ws_load_id(src, tile0 + tile_stride, tg, n_live, n_tiles));
+            id_after = ws_load_id(src, tile0 + 2 * tile_stride, tg, n_live, n_tiles);
+            mv_next = publish_tables(r0);
+        }
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride, ++k) {
             const uint32_t par = (uint32_t)(k & 1);
             WS_ACC(15, tc, prof_c);
             mbar_wait_parity(smem_u32(full + g), par);
             WS_ACC(8, tc, prof_c);
             if (prof_c) { g_ws_prof_tiles(); }
-            const float4 mv = *reinterpret_cast<const float4*>(gs + L::META + tg * 4);
+            const float4 mv = ctab ? mv_next : *reinterpret_cast<const float4*>(gs + L::META + tg * 4);
             const int id32 = (int)__float_as_uint(mv.x);
             const int64_t id = id32;
             {
@@ -552,6 +652,12 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
             mbar_arrive(smem_u32(sfree + g));       // row and meta are in registers / TMEM: the gather warps may refill the stage
             group_sync(u.group);
             if (leader) { umma_mma<3>(u, bW1, C, false); umma_commit(u); }
+            if (ctab && tile + tile_stride < n_tiles) {      // tables of the next tile, in the shadow of the first layer
+                const WsRaw r = raw_next;
+                raw_next = ws_load_raw(src, id_after);
+                id_after = ws_load_id(src, tile + 3 * tile_stride, tg, n_live, n_tiles);
+                mv_next = publish_tables(r);
+            }
             umma_wait(u);
             uint32_t m1[2], m2[2];
 #pragma unroll
