@@ -598,6 +598,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--option", action="append", help="library experiment switch name=value (tt_set_option); not for headline numbers")
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + list(OP_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
@@ -627,6 +628,9 @@ def main():
     from triplaneturbo_b200 import ops
     if args.kernels is not None:
         ops.set_impl(args.kernels)
+    for kv in args.option or []:          # experiment switches of the library (tt_set_option), e.g. --option scatter=2
+        k_, v_ = kv.split("=")
+        ops.set_option(k_, int(v_))
     if args.workload in OP_WORKLOADS:
         if rank == 0:
             run_op(args, real_stdout)
