@@ -3,5 +3,5 @@
 set -euo pipefail
 here="$(cd "$(dirname "$0")" && pwd)"
 src="$here/../../triplaneturbo_b200/csrc/tt_kernels.cu"
-g++ -O2 -std=c++20 -ffp-contract=off -fPIC -shared -pthread -DTT_EMUL -include "$here/cuda_emul.h" \
+g++ -O2 -std=c++20 -ffp-contract=off -fPIC -shared -pthread -DTT_EMUL ${TT_EMUL_FLAGS:-} -include "$here/cuda_emul.h" \
     -x c++ "$src" -o "$here/libtt_emul.so"

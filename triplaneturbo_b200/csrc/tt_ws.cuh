@@ -35,6 +35,9 @@ constexpr int WS_NBUF = 2;                              // stage buffers per con
 // 65536 / 384 -> 168 registers per thread; the gather warpgroup grows to WS_REG_M (more loads in flight: the gather is
 // bound by loads in flight, tools/tma_gather_probe.cu), the two consumer warpgroups shrink to WS_REG_C.
 // 128 * 232 + 256 * 136 = 64512 = 384 * 168.
+#ifndef WS_CTAB_NORMAL
+#define WS_CTAB_NORMAL 0        // consumer-made tap tables also in the kernel WITH the normal (experiment: DESIGN 3.5 item 12)
+#endif
 #ifndef WS_GEO_NMG
 #define WS_GEO_NMG 1            // gather warpgroups of k_geo_ws: 1 (serves both consumer groups in turn) or 2 (one per consumer group)
 #endif
@@ -123,8 +126,8 @@ struct GeoWs {
     // CTAB (kernels without the normal): the CONSUMER groups compute the tap tables of their next tile (thread = point, in
     // the shadow of their MMA round trips) and hand them to the gather warps through `tables_ready`; the gather warps only
     // gather.  Group 0's tables live in MTAB, group 1's in CTAB1.
-    static constexpr bool CTAB = !NORMAL && WS_GEO_NMG == 1;
     static constexpr int CTAB1 = BARS + 2 * 4 * WS_CG + 4;
+    static constexpr bool CTAB = WS_GEO_NMG == 1 && (!NORMAL || (WS_CTAB_NORMAL && (size_t)(CTAB1 + MTAB_FLOATS) * 4 <= 227 * 1024));
     static constexpr int TOTAL0 = CTAB1 + (CTAB ? MTAB_FLOATS : 0);
     static_assert(CTAB1 % 4 == 0, "table buffers are read as 16-byte vectors");
     static_assert(BARS % 2 == 0, "mbarriers must be 8-byte aligned");
@@ -307,6 +310,8 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
                 mbar_wait_parity(smem_u32(sfree + g), par ^ 1u);        // the group has taken its previous tile out of the stage
                 WS_ACC(0, tm, prof_m);
                 float* stage = gs + L::STAGE;
+                const float* t_cx = ct + L::TAP_CX; const float* t_cy = ct + L::TAP_CY; (void)t_cx; (void)t_cy;
+                float* vt = NORMAL ? vcta + (size_t)(g * 2 + (int)par) * L::VTILE : nullptr;
                 constexpr int JB = WS_GATHER_JB, ITEMS = 128 * U;
 #pragma unroll 1
                 for (int i0 = mt; i0 < ITEMS; i0 += JB * WS_M) {
@@ -329,6 +334,9 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
                     for (int b = 0; b < JB; ++b) {
                         if (i0 + b * WS_M >= ITEMS) continue;
                         float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 V[3];
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) V[a] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int kk = 0; kk < 3; ++kk) {
                             const float4 w4 = *reinterpret_cast<const float4*>(t_w + pt[b] * 12 + kk * 4);
@@ -341,10 +349,31 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
                                 sacc.z = fmaf(ww[t], q.z, sacc.z); sacc.w = fmaf(ww[t], q.w, sacc.w);
                             }
                             e.x += sacc.x; e.y += sacc.y; e.z += sacc.z; e.w += sacc.w;
+                            if (NORMAL) {
+                                const float4 x4 = *reinterpret_cast<const float4*>(t_cx + pt[b] * 12 + kk * 4);
+                                const float4 y4 = *reinterpret_cast<const float4*>(t_cy + pt[b] * 12 + kk * 4);
+                                const float cx[4] = {x4.x, x4.y, x4.z, x4.w}, cy[4] = {y4.x, y4.y, y4.z, y4.w};
+                                const int ax = kk == 2 ? 2 : 0, ay = kk == 1 ? 2 : 1;          // plane_ax / plane_ay, compile time
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const float4 q = v[b][kk * 4 + t];
+                                    V[ax].x = fmaf(cx[t], q.x, V[ax].x); V[ax].y = fmaf(cx[t], q.y, V[ax].y);
+                                    V[ax].z = fmaf(cx[t], q.z, V[ax].z); V[ax].w = fmaf(cx[t], q.w, V[ax].w);
+                                    V[ay].x = fmaf(cy[t], q.x, V[ay].x); V[ay].y = fmaf(cy[t], q.y, V[ay].y);
+                                    V[ay].z = fmaf(cy[t], q.z, V[ay].z); V[ay].w = fmaf(cy[t], q.w, V[ay].w);
+                                }
+                            }
                         }
                         *reinterpret_cast<float4*>(stage + pt[b] * SP + ch[b] * 4) = e;
+                        if (NORMAL) {
+#pragma unroll
+                            for (int a = 0; a < 3; ++a) *reinterpret_cast<float4*>(vt + L::vidx(pt[b], a, ch[b])) = V[a];
+                        }
                     }
                 }
+#ifndef TT_EMUL
+                if (NORMAL) __threadfence_block();
+#endif
                 mbar_arrive(smem_u32(full + g));
                 WS_ACC(2, tm, prof_m);
             }
@@ -620,6 +649,13 @@ __global__ void __launch_bounds__(WS_GEO_THREADS, 1) k_geo_ws(const float* __res
                 w4.x = i0 ? tp.w[0] : 0.f; w4.y = i1 ? tp.w[1] : 0.f; w4.z = i2 ? tp.w[2] : 0.f; w4.w = i3 ? tp.w[3] : 0.f;
                 *reinterpret_cast<int4*>(t_o + tg * 12 + kk * 4) = o4;
                 *reinterpret_cast<float4*>(t_w + tg * 12 + kk * 4) = w4;
+                if (NORMAL) {   // d enc / d ix, d enc / d iy coefficients of the four texels (as the gather warps' tables)
+                    float4 x4, y4;
+                    x4.x = i0 ? -tp.wy0 : 0.f; x4.y = i1 ? tp.wy0 : 0.f; x4.z = i2 ? -tp.wy1 : 0.f; x4.w = i3 ? tp.wy1 : 0.f;
+                    y4.x = i0 ? -tp.wx0 : 0.f; y4.y = i1 ? -tp.wx1 : 0.f; y4.z = i2 ? tp.wx0 : 0.f; y4.w = i3 ? tp.wx1 : 0.f;
+                    *reinterpret_cast<float4*>(ct + L::TAP_CX + tg * 12 + kk * 4) = x4;
+                    *reinterpret_cast<float4*>(ct + L::TAP_CY + tg * 12 + kk * 4) = y4;
+                }
             }
             reinterpret_cast<uint32_t*>(ct + L::PBASE)[tg] = (uint32_t)prompt;
             mbar_arrive(smem_u32(tready + g));
