@@ -66,7 +66,8 @@ typedef struct {
     int32_t flags;           /* TT_FLAG_* */
     int32_t image_h, image_w; /* optional hint: the rays are [B][image_h][image_w] images (row-major pixels).  0 = unknown.
                                  tt_render_bwd then visits the samples in PATCH order (4x4 neighbouring rays x 8 samples per
-                                 tile), which lets the scatter kernels merge the taps of a tile; results do not depend on it */
+                                 tile) and merges the taps of a tile on chip before the vector reductions (colour backward
+                                 430 -> 379 ms at config 3); results do not depend on it beyond the summation order */
 } tt_config;
 #define TT_FLAG_PRECISE_BWD 2  /* tt_render_bwd / tt_geometry_bwd: run the colour decoder's backward layers as 3xTF32 (fp32-equivalent)
                                   instead of single-pass TF32; one 128-thread group per CTA fits then (slower) */
@@ -81,11 +82,12 @@ int tt_device_ok(void);
  * kernels.  Both are CUDA; parity tests run both. */
 int tt_set_impl(int impl);
 int tt_get_impl(void);
-/* Experiment switches of the backward (defaults are the measured-fastest settings):
- *   "scatter"     -1 auto (default), 0 plain, 1 run-length merged, 2 tile-merged hidden-gradient scatter
- *   "patch_lists"  0 (default) / 1: with tt_config.image_h/w set, tt_render_bwd visits the samples in 4x4-pixel patch order
+/* Switches of the backward and of the field query; results are identical up to the summation order:
+ *   "patch_lists"  1 (default) / 0: with tt_config.image_h/w set, tt_render_bwd visits the samples in 4x4-pixel patch order
+ *   "scatter"     -1 auto (default: tile-merged on patch-ordered lists, else run-length merged for rays of >= 256 samples,
+ *                  else plain), 0 plain, 1 run-length merged, 2 tile-merged hidden-gradient scatter
  *   "grid_lines"   0 (default) / 1: tt_geometry_fwd on the regular grid gathers z-lines instead of 12 taps per point
- * Initial values come from the environment (TT_SCATTER, TT_PATCH_LISTS).  Results are identical up to the summation order. */
+ * Initial values come from the environment (TT_SCATTER, TT_PATCH_LISTS). */
 int tt_set_option(const char* name, int value);
 
 /* ---- decoder weights -----------------------------------------------------------------

@@ -192,14 +192,14 @@ def test_render_forward_backward(em, name):
     else:                              # ... or through the per-sample sdf_grad output, like the reference's system
         g_sdf_grad = (0.1 * 2.0 * (nrm - 1.0) * sg / nrm).numpy()
     g_acc, = torch.autograd.grad(loss, acc)
-    if H % 4 == 0 and W % 4 == 0:           # opt-in experiment: patch-ordered sample lists (k_patch_lists) + tile-merged
-        cfg.image_h, cfg.image_w = H, W     # scatter; other fixtures run the default plain / run-length scatter
+    if H % 4 == 0 and W % 4 == 0:           # image-shape hint: patch-ordered sample lists (k_patch_lists) + tile-merged
+        cfg.image_h, cfg.image_w = H, W     # scatter; the other fixtures run the plain / run-length scatter on ray order
         em.set_option("patch_lists", 1); em.set_option("scatter", 2)
     try:
         gplanes, gw, gis = em.render_bwd(planes, wp, cfg, o, d, fx["t_starts"].numpy(), fx["t_ends"].numpy(), fwd,
                                          g_acc.numpy(), g_sdf_grad=g_sdf_grad, rgb_scale=pc.rgb_grad_shrink)
     finally:
-        em.set_option("patch_lists", 0); em.set_option("scatter", -1)
+        em.set_option("patch_lists", 1); em.set_option("scatter", -1)
     assert rel_err(torch.from_numpy(em.repack_bwd(gplanes)), fx["grad_space_cache"]) < GTOL
     names = [f"grad_w_sdf_{i}" for i in range(3)] + [f"grad_w_feature_{i}" for i in range(3)]
     for n, g in zip(names, gw):

@@ -1,7 +1,8 @@
-"""Opt-in experiment paths (include/triplane_b200.h tt_set_option) against the default kernels on the GPU: they compute the
-same sums in another order, so gradients agree to the accuracy of fp32 reductions and forward outputs to 1e-6.
-  * "patch_lists" + "scatter" = 2: patch-ordered sample lists (k_patch_lists) + tile-merged hidden-gradient scatter
-  * "scatter" = 0 / 1: plain / run-length merged scatter
+"""Switchable paths (include/triplane_b200.h tt_set_option) against each other on the GPU: they compute the same sums in
+another order, so gradients agree to the accuracy of fp32 reductions and forward outputs to 1e-6.
+  * "patch_lists" + "scatter" = 2 (the default when the image shape is known): patch-ordered sample lists (k_patch_lists)
+    + tile-merged hidden-gradient scatter
+  * "scatter" = 0 / 1: plain / run-length merged scatter, "patch_lists" = 0: ray-ordered lists
   * "grid_lines": z-line gather of the regular isosurface grid (ws_grid_segment)"""
 import pytest
 import torch
@@ -17,7 +18,7 @@ DEV = "cuda"
 @pytest.fixture(autouse=True)
 def _defaults():
     yield
-    for k, v in (("scatter", -1), ("patch_lists", 0), ("grid_lines", 0)):
+    for k, v in (("scatter", -1), ("patch_lists", 1), ("grid_lines", 0)):       # the library defaults
         ops.set_option(k, v)
     ops.set_impl(2)
 

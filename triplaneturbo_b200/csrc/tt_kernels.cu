@@ -151,8 +151,8 @@ static int launch_tex_decoder(const float* planes, const float* wpack, const tt_
     return check_launch("k_tex_tc");
 }
 
-// experiment switches (tt_set_option; initial values from the environment): "scatter" = -1 auto, 0 plain, 1 run-length,
-// 2 tile-merged hidden-gradient scatter; "patch_lists" = 1: patch-ordered sample lists when the image shape is known;
+// switches (tt_set_option; initial values from the environment): "scatter" = -1 auto, 0 plain, 1 run-length,
+// 2 tile-merged hidden-gradient scatter; "patch_lists" = 1 (default): patch-ordered sample lists when the image shape is known;
 // "grid_lines" = 1: z-line gather of the regular isosurface grid (ws_grid_segment, tt_ws.cuh)
 static int g_opt_scatter = -2, g_opt_patch = -1, g_opt_grid_lines = 0;
 static int scatter_mode() {
@@ -160,7 +160,7 @@ static int scatter_mode() {
     return g_opt_scatter;
 }
 static bool patch_mode() {
-    if (g_opt_patch < 0) { const char* e = getenv("TT_PATCH_LISTS"); g_opt_patch = e ? (atoi(e) != 0) : 0; }
+    if (g_opt_patch < 0) { const char* e = getenv("TT_PATCH_LISTS"); g_opt_patch = e ? (atoi(e) != 0) : 1; }
     return g_opt_patch != 0;
 }
 // colour backward: SC = scatter variant of the hidden gradient, P3 = 3xTF32 layers (TT_FLAG_PRECISE_BWD)
@@ -1117,7 +1117,8 @@ static size_t hid_floats(const tt_config* cfg) {      // hidden-gradient planes 
 static int launch_point_bwd(const float* planes, const float* wpack, const tt_config* cfg, const PtSrc& src, int64_t N,
                             const float* gs, const float* u, const float* gf, const uint64_t* tex_masks, float* gplanes,
                             float* gw, float* hid, cudaStream_t st, const int* geo_list = nullptr,
-                            const int* geo_count = nullptr, const int* tex_list = nullptr, const int* tex_count = nullptr) {
+                            const int* geo_count = nullptr, const int* tex_list = nullptr, const int* tex_count = nullptr,
+                            bool patch_ordered = false) {
     const int64_t blocks = (N + TPB - 1) / TPB;
     if (blocks > 2147483647LL) return fail(TT_E_ARG, "too many sample points%s (%lld)", "", N);
     if (g_impl >= 1 && N < 2147483647LL) {
@@ -1144,11 +1145,11 @@ static int launch_point_bwd(const float* planes, const float* wpack, const tt_co
                     // colour branch: per-sample kernel scatters the 64-wide hidden gradient, then two dense products
                     if (cudaMemsetAsync(hid, 0, hid_floats(cfg) * sizeof(float), st) != cudaSuccess) return fail(TT_E_CUDA, "cudaMemsetAsync failed%s", "");
                     ts.index = tex_list; ts.count = tex_count;
-                    // scatter of the hidden gradient: run-length merged for long rays (consecutive samples share texel cells),
-                    // plain otherwise; TT_SCATTER=0|1|2 forces plain / run-length / tile-merged (the
-                    // tile-merged form cuts the reductions 4-6x on patch-ordered lists but costs as many issue slots as it saves)
+                    // scatter of the hidden gradient: tile-merged when the lists are patch-ordered (a texel then receives ~6 of a
+                    // tile's taps: DESIGN 3.5 item 10), else run-length merged for long rays (consecutive samples share texel
+                    // cells) or plain; tt_set_option("scatter", 0|1|2) forces a variant
                     int sc = scatter_mode();
-                    if (sc < 0) sc = (!src.points && src.rs.S >= 256) ? 1 : 0;
+                    if (sc < 0) sc = patch_ordered ? 2 : ((!src.points && src.rs.S >= 256) ? 1 : 0);
                     if ((int64_t)cfg->P * 3 * cfg->R * cfg->R >= (1LL << MergeWs::KEY_BITS) && sc == 2) sc = 0;       // texel numbers must fit the merge keys
                     const bool p3 = (cfg->flags & TT_FLAG_PRECISE_BWD) != 0 && (size_t)BwdTexSmem<kC, true>::TOTAL * 4 <= kMaxSmem;
                     int e = 0;
@@ -1242,7 +1243,7 @@ int tt_render_bwd(const float* planes, const float* wpack, const tt_config* cfg,
     float* hid = scratch + round4((size_t)N * 9 + 16 + (size_t)n_rays * 2 * (size_t)ray_chunks(S));
     if (!geo_list) masks = nullptr;      // the forward ran the SIMT kernels (no masks were written): SIMT backward
     return launch_point_bwd(planes, wpack, cfg, src, N, gs, u, gf, masks, gplanes, gw, hid, st, geo_list, counts, tex_list,
-                            counts ? counts + 1 : (const int*)nullptr);
+                            counts ? counts + 1 : (const int*)nullptr, patch_lists);
 }
 
 size_t tt_geometry_bwd_scratch_floats(const tt_config* cfg, int64_t n_points) { return round4((size_t)n_points * 18 + 16) + hid_floats(cfg); }

@@ -272,46 +272,57 @@ __device__ __forceinline__ void coop_scatter_merged(float* __restrict__ dst, int
         if (tg == TC_GROUP - 1) misc[4] = off;            // entries of the tile
     }
     group_sync(group);
+    // entry = (texel | point << 24, weight); the FIRST entry of a bucket carries the sign bit in its weight (bilinear weights
+    // are >= 0), which is all the walk below needs to find the runs
 #pragma unroll
     for (int j = 0; j < NT; ++j)
         if (hpos[j] >= 0)
-            ent[hcnt[hpos[j]] + aux[j]] = make_int2(key_of(j >> 2, j & 3) | (tg << KB), (int)__float_as_uint(w_of(j >> 2, j & 3)));
+            ent[hcnt[hpos[j]] + aux[j]] = make_int2(key_of(j >> 2, j & 3) | (tg << KB),
+                                                    (int)(__float_as_uint(w_of(j >> 2, j & 3)) | (aux[j] == 0 ? 0x80000000u : 0u)));
+    {   // pad the list to a multiple of 4 entries (weight 0, no run start)
+        const int total = misc[4];
+        if (tg < 4 && total + tg < ((total + 3) & ~3)) ent[total + tg] = make_int2(0, 0);
+    }
     group_sync(group);
     WS_ACC(26, tm_, prof);
-    // The entry list is cut into TC_GROUP / CH equal ranges; thread (range, 16-byte chunk) walks its range, sums weight x
-    // staged row while the texel stays the same and issues ONE vector reduction per run (a bucket that straddles two
-    // ranges costs two).  Entries are read four at a time: their loads do not depend on the running sum.
+    // The entry list is cut into TC_GROUP / CH ranges of whole 4-entry blocks; thread (range, 16-byte chunk) walks its range,
+    // sums weight x staged row while the texel stays the same and issues ONE vector reduction per run (a bucket that straddles
+    // two ranges costs two).  Four entries are loaded at a time: their loads do not depend on the running sum.
     {
         constexpr int NRANGE = TC_GROUP / CH;
         const int total = misc[4];
         if (prof) g_ws_prof_add(28, (unsigned long long)total);
+        const int blocks = (total + 3) >> 2;
         const int r = tg / CH, ch = tg - r * CH;
-        const int e0 = (int)(((long long)total * r) / NRANGE), e1 = (int)(((long long)total * (r + 1)) / NRANGE);
-        int cur = -1;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int e0 = ((blocks * r) / NRANGE) << 2, e1 = ((blocks * (r + 1)) / NRANGE) << 2;
         const float* srow = stage + ch * 4;
         float* drow = dst + ch * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cur = -1;
+        if (e0 < e1) { const int2 f = ent[e0]; cur = f.y < 0 ? -1 : (f.x & ((1 << KB) - 1)); }      // range starts inside a bucket
+        int2 en[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) en[q] = ent[e0 + q];             // (the list has 8 entries of slack: reading ahead is safe)
 #pragma unroll 1
         for (int e = e0; e < e1; e += 4) {
-            int2 en[4]; float4 v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) en[q] = ent[e + q < e1 ? e + q : e1 - 1];
+            float4 v[4]; int2 nx[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const float4*>(srow + ((uint32_t)en[q].x >> KB) * stage_stride);
 #pragma unroll
+            for (int q = 0; q < 4; ++q) nx[q] = ent[e + 4 + q];      // next block, one iteration ahead of its use
+#pragma unroll
             for (int q = 0; q < 4; ++q) {
-                if (e + q < e1) {
-                    const int key = en[q].x & ((1 << KB) - 1);
-                    const float w = __uint_as_float((uint32_t)en[q].y);
-                    if (key != cur) {
-                        if (cur >= 0) red_add4(drow + (size_t)cur * texel_stride, acc);
-                        cur = key; acc = make_float4(w * v[q].x, w * v[q].y, w * v[q].z, w * v[q].w);
-                    } else {
-                        acc.x = fmaf(w, v[q].x, acc.x); acc.y = fmaf(w, v[q].y, acc.y);
-                        acc.z = fmaf(w, v[q].z, acc.z); acc.w = fmaf(w, v[q].w, acc.w);
-                    }
+                if (en[q].y < 0) {                                   // a new texel starts: flush the finished run
+                    if (cur >= 0) red_add4(drow + (size_t)cur * texel_stride, acc);
+                    cur = en[q].x & ((1 << KB) - 1);
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                const float w = fabsf(__uint_as_float((uint32_t)en[q].y));
+                acc.x = fmaf(w, v[q].x, acc.x); acc.y = fmaf(w, v[q].y, acc.y);
+                acc.z = fmaf(w, v[q].z, acc.z); acc.w = fmaf(w, v[q].w, acc.w);
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) en[q] = nx[q];
         }
         if (cur >= 0) red_add4(drow + (size_t)cur * texel_stride, acc);
     }
