@@ -196,7 +196,8 @@ __device__ __forceinline__ void coop_scatter_rl(float* __restrict__ dst, size_t 
 // Workspace: MergeWs::TOTAL ints of shared memory per group (aliases an operand tile that is free during the scatter).
 struct MergeWs {
     static constexpr int HN = 2048, MAXT = 1536;                 // hash positions; taps of a tile (128 points x 3 planes x 4)
-    static constexpr int KEY = 0, CNT = KEY + HN, ENT = CNT + HN, MISC = ENT + 2 * MAXT + 16;
+    static constexpr int EB = 4;                                 // entries per block of the walk (list padded to it, read one block ahead; 8: no gain)
+    static constexpr int KEY = 0, CNT = KEY + HN, ENT = CNT + HN, MISC = ENT + 2 * MAXT + 4 * EB;
     static constexpr int TOTAL = MISC + 8;
     static constexpr int KEY_BITS = 24;                          // texel numbers must fit (the point index rides above them)
 };
@@ -279,39 +280,40 @@ __device__ __forceinline__ void coop_scatter_merged(float* __restrict__ dst, int
         if (hpos[j] >= 0)
             ent[hcnt[hpos[j]] + aux[j]] = make_int2(key_of(j >> 2, j & 3) | (tg << KB),
                                                     (int)(__float_as_uint(w_of(j >> 2, j & 3)) | (aux[j] == 0 ? 0x80000000u : 0u)));
-    {   // pad the list to a multiple of 4 entries (weight 0, no run start)
+    constexpr int EB = MergeWs::EB;
+    {   // pad the list to a multiple of EB entries (weight 0, no run start)
         const int total = misc[4];
-        if (tg < 4 && total + tg < ((total + 3) & ~3)) ent[total + tg] = make_int2(0, 0);
+        if (tg < EB && total + tg < ((total + EB - 1) / EB) * EB) ent[total + tg] = make_int2(0, 0);
     }
     group_sync(group);
     WS_ACC(26, tm_, prof);
-    // The entry list is cut into TC_GROUP / CH ranges of whole 4-entry blocks; thread (range, 16-byte chunk) walks its range,
+    // The entry list is cut into TC_GROUP / CH ranges of whole EB-entry blocks; thread (range, 16-byte chunk) walks its range,
     // sums weight x staged row while the texel stays the same and issues ONE vector reduction per run (a bucket that straddles
-    // two ranges costs two).  Four entries are loaded at a time: their loads do not depend on the running sum.
+    // two ranges costs two).  A block's staged rows are loaded together, its entries one block ahead.
     {
         constexpr int NRANGE = TC_GROUP / CH;
         const int total = misc[4];
         if (prof) g_ws_prof_add(28, (unsigned long long)total);
-        const int blocks = (total + 3) >> 2;
+        const int blocks = (total + EB - 1) / EB;
         const int r = tg / CH, ch = tg - r * CH;
-        const int e0 = ((blocks * r) / NRANGE) << 2, e1 = ((blocks * (r + 1)) / NRANGE) << 2;
+        const int e0 = ((blocks * r) / NRANGE) * EB, e1 = ((blocks * (r + 1)) / NRANGE) * EB;
         const float* srow = stage + ch * 4;
         float* drow = dst + ch * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int cur = -1;
         if (e0 < e1) { const int2 f = ent[e0]; cur = f.y < 0 ? -1 : (f.x & ((1 << KB) - 1)); }      // range starts inside a bucket
-        int2 en[4];
+        int2 en[EB];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) en[q] = ent[e0 + q];             // (the list has 8 entries of slack: reading ahead is safe)
+        for (int q = 0; q < EB; ++q) en[q] = ent[e0 + q];            // (the list has 2 blocks of slack: reading ahead is safe)
 #pragma unroll 1
-        for (int e = e0; e < e1; e += 4) {
-            float4 v[4]; int2 nx[4];
+        for (int e = e0; e < e1; e += EB) {
+            float4 v[EB]; int2 nx[EB];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const float4*>(srow + ((uint32_t)en[q].x >> KB) * stage_stride);
+            for (int q = 0; q < EB; ++q) v[q] = *reinterpret_cast<const float4*>(srow + ((uint32_t)en[q].x >> KB) * stage_stride);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) nx[q] = ent[e + 4 + q];      // next block, one iteration ahead of its use
+            for (int q = 0; q < EB; ++q) nx[q] = ent[e + EB + q];    // next block, one iteration ahead of its use
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < EB; ++q) {
                 if (en[q].y < 0) {                                   // a new texel starts: flush the finished run
                     if (cur >= 0) red_add4(drow + (size_t)cur * texel_stride, acc);
                     cur = en[q].x & ((1 << KB) - 1);
@@ -322,7 +324,7 @@ __device__ __forceinline__ void coop_scatter_merged(float* __restrict__ dst, int
                 acc.z = fmaf(w, v[q].z, acc.z); acc.w = fmaf(w, v[q].w, acc.w);
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) en[q] = nx[q];
+            for (int q = 0; q < EB; ++q) en[q] = nx[q];
         }
         if (cur >= 0) red_add4(drow + (size_t)cur * texel_stride, acc);
     }
