@@ -10,7 +10,9 @@
 //   * SDF branch: dW2 and dw3 both come out of one accumulator Q = Σ m2 ⊗ h̃1 (k_bwd_geo_tc),
 //   * colour branch: first-layer gradients through hidden-gradient planes (k_bwd_tex_tc, k_hid_planes, k_hid_wgrad).
 // Plane gradients: cooperative scatter (consecutive lanes = consecutive 16-byte chunks of one texel) with
-// red.global.add.v4.f32; run-length merged over consecutive samples for the 64-wide colour scatter.
+// red.global.add.v4.f32.  The 64-wide colour scatter merges a tile's taps per texel on chip first when the sample lists are
+// patch-ordered (coop_scatter_merged + k_patch_lists, the default with an image-shaped ray batch), else run-length merges
+// consecutive samples of long rays (coop_scatter_rl) or scatters plainly.
 #pragma once
 #include "tt_tc.cuh"
 

@@ -4,15 +4,17 @@
 // the normal pass were serialised per group and their times ADDED UP (DESIGN.md "Phase anatomy").  Here a CTA has a
 // dedicated memory warpgroup and two consumer groups that overlap through mbarrier hand-offs:
 //
-//   gather warps (threads 0..127, "M group")   for each consumer group in turn: sample positions + bilinear tap tables of
-//                                              the group's next 128-point tile, cooperative gather of the blended encoding
-//                                              (consecutive lanes = consecutive 16-byte chunks of a channel-last texel,
-//                                              24 loads in flight per lane) into the group's stage; and, when a group has
-//                                              produced d sdf / d enc, the normal pass: second cooperative pass over the 12
-//                                              taps (4 lanes per point) -> d sdf / d x
+//   gather warps (threads 0..127, "M group")   for each consumer group in turn: cooperative gather of the blended encoding of
+//                                              the group's next 128-point tile (consecutive lanes = consecutive 16-byte
+//                                              chunks of a channel-last texel, 36 loads in flight per lane) into the
+//                                              group's stage; with the normal also the tangent rows V_a = d enc / d x_a
+//                                              (same texels, other weights) into an L2-resident scratch.  The tap tables
+//                                              (sample -> position -> 12 taps and weights) are made by the gather warps
+//                                              in the kernel with the normal, by the CONSUMER groups in the others (CTAB)
 //   2 consumer groups (2 x 128 threads)        thread = sample point = TMEM lane: the decoder layers on tcgen05 (3xTF32, A
-//                                              operand in TMEM, accumulator read back in 32-column halves to keep the
-//                                              register count at 168), heads, outputs.
+//                                              operand in TMEM, accumulator read back in 32-column halves), heads,
+//                                              outputs; normal = unit-seed adjoint (W2^T, W1^T layers) . tangent rows;
+//                                              field query (DEFORM): both decoders' first layers as one N = 128 MMA chain
 // While one group runs its layers the gather warps serve the other group, so the load path and the tensor pipe are busy
 // at the same time (round 1: `mem_lock` spin lock between two groups that each did their own gathers).
 //
@@ -22,6 +24,8 @@
 //   * tangent-mode normal (rows e, de/dx, de/dy, de/dz through two layers, no second gather, no transposed weights):
 //     parity-green but 2x the epilogue rows and MMAs per point; the kernel is issue-bound and ran 20 % SLOWER than round 1
 //     (profiles/r02_ws_tangent_*.txt).
+//   * adjoint normal with a SECOND gather of the 12 taps once d sdf / d enc is known, two gather warpgroups, consumer-made
+//     tables in the kernel with the normal, regular-grid z-lines: DESIGN.md 3.5 items 3, 6, 11, 12.
 #pragma once
 #include "tt_tc.cuh"
 
