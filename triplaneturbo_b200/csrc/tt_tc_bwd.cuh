@@ -648,21 +648,36 @@ k_bwd_tex_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
 
     const bool prof = blockIdx.x == 0 && tid == 0; (void)prof;
     WS_T0(tp_);
-    for (int64_t tile = (int64_t)blockIdx.x * G + group; tile < n_tiles; tile += (int64_t)gridDim.x * G) {
-        const int64_t slot = tile * TC_GROUP + tg;
-        const bool valid = slot < n_live;
-        const int64_t id = valid ? (src.index ? (int64_t)src.index[slot] : slot) : 0;
-        float gf[3] = {0.f, 0.f, 0.f};
-        if (valid) { gf[0] = gf_i[id * 3]; gf[1] = gf_i[id * 3 + 1]; gf[2] = gf_i[id * 3 + 2]; }
+    // Per-sample inputs of a tile (seed, ReLU masks, raw position words) are loaded ONE tile ahead and the sample id two
+    // tiles ahead: their dependent global loads (id -> seed / masks / ray) would otherwise be exposed at every tile start
+    // (anatomy: 3.1 k of 36 k cycles per tile).
+    struct Pre { WsRaw raw; float gf[3]; uint64_t m1, m2; };
+    const int64_t tstride = (int64_t)gridDim.x * G, tile0 = (int64_t)blockIdx.x * G + group;
+    auto load_pre = [&](int id) {
+        Pre q; q.raw = ws_load_raw(src, id); q.gf[0] = q.gf[1] = q.gf[2] = 0.f; q.m1 = q.m2 = 0ull;
+        if (id >= 0) {
+            q.gf[0] = gf_i[(int64_t)id * 3]; q.gf[1] = gf_i[(int64_t)id * 3 + 1]; q.gf[2] = gf_i[(int64_t)id * 3 + 2];
+            q.m1 = masks[(int64_t)id * 4]; q.m2 = masks[(int64_t)id * 4 + 1];
+        }
+        return q;
+    };
+    Pre pre_next = load_pre(ws_load_id(src, tile0, tg, n_live, n_tiles));
+    int id_after = ws_load_id(src, tile0 + tstride, tg, n_live, n_tiles);
+    for (int64_t tile = tile0; tile < n_tiles; tile += tstride) {
+        const Pre cur = pre_next;
+        pre_next = load_pre(id_after);                                  // in flight during this tile
+        id_after = ws_load_id(src, tile + 2 * tstride, tg, n_live, n_tiles);
+        const bool valid = cur.raw.id >= 0;
+        const float gf[3] = {cur.gf[0], cur.gf[1], cur.gf[2]};
         const bool active = valid && (gf[0] != 0.f || gf[1] != 0.f || gf[2] != 0.f);
         if (prof) g_ws_prof_tiles();
         // the ReLU masks are the forward's (3xTF32) masks: a single-pass recompute may flip units near zero
-        const uint64_t m1 = active ? masks[id * 4] : 0ull, m2 = active ? masks[id * 4 + 1] : 0ull;
+        const uint64_t m1 = active ? cur.m1 : 0ull, m2 = active ? cur.m2 : 0ull;
         int prompt = 0;
         float p[3];
         {
             float x[3] = {0.f, 0.f, 0.f};
-            if (active) tc_point(src, id, x, prompt);
+            if (active) ws_point_from_raw(src, cur.raw, x, prompt);
 #pragma unroll
             for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
         }

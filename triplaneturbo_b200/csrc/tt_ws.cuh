@@ -173,68 +173,6 @@ __device__ __forceinline__ void ws_axis_tap(float g, int R, int& i0, float (&w)[
     i0 = (int)fminf(fmaxf(x0f, -2.f), fR + 2.f);
 }
 
-// Sample of a gather job, prefetched one job ahead as RAW loaded words: the arithmetic that turns them into a position
-// runs one job later, so the global-load latency (sample id -> interval edges / ray) hides behind the previous gather.
-struct WsRaw { float v[8]; int id; };
-__device__ __forceinline__ int ws_load_id(const TcSrc& src, int64_t tile, int mt, int64_t n_live, int64_t n_tiles) {
-    if (tile >= n_tiles) return -1;
-    const int64_t slot = tile * TC_GROUP + mt;
-    if (slot >= n_live) return -1;
-    return src.index ? src.index[slot] : (int)slot;
-}
-__device__ __forceinline__ WsRaw ws_load_raw(const TcSrc& s, int id) {
-    WsRaw r; r.id = id;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
-    if (id < 0) return r;
-    if (s.mode == 0) {
-        r.v[0] = s.points[(int64_t)id * 3]; r.v[1] = s.points[(int64_t)id * 3 + 1]; r.v[2] = s.points[(int64_t)id * 3 + 2];
-    } else if (s.mode == 1 || s.mode == 2) {
-        int64_t ray;
-        if (s.mode == 1) {
-            ray = id / s.rs.S; const int i = id - (int)ray * s.rs.S;
-            r.v[0] = s.rs.t_starts[ray * s.rs.t_stride + i]; r.v[1] = s.rs.t_ends[ray * s.rs.t_stride + i];
-        } else {
-            ray = id / s.n_imp;
-            r.v[0] = s.jitter0 ? s.jitter0[ray] : 0.f;
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { r.v[2 + a] = s.rs.rays_o[ray * 3 + a]; r.v[5 + a] = s.rs.rays_d[ray * 3 + a]; }
-    }
-    return r;
-}
-// same arithmetic as tc_point (tt_tc.cuh), on the prefetched words
-__device__ __forceinline__ void ws_point_from_raw(const TcSrc& s, const WsRaw& r, float (&x)[3], int& prompt) {
-    x[0] = x[1] = x[2] = 0.f; prompt = 0;
-    if (r.id < 0) return;
-    if (s.mode == 0) {
-        x[0] = r.v[0]; x[1] = r.v[1]; x[2] = r.v[2];
-        prompt = s.M > 0x7fffffffLL ? 0 : (int)((uint32_t)r.id / (uint32_t)s.M);
-    } else if (s.mode == 3) {
-        // (sample ids are 32-bit here and M = rr^3 <= N < 2^31: 32-bit divisions, a 64-bit one costs ~100 instructions)
-        const uint32_t M = (uint32_t)s.M, rr = (uint32_t)s.grid_res;
-        prompt = (int)((uint32_t)r.id / M);
-        const uint32_t v = (uint32_t)r.id - (uint32_t)prompt * M, xi = v / (rr * rr), rem = v - xi * rr * rr, yi = rem / rr;
-        x[0] = grid_coord_tc((int)xi, (int)rr); x[1] = grid_coord_tc((int)yi, (int)rr);
-        x[2] = grid_coord_tc((int)(rem - yi * rr), (int)rr);
-    } else {
-        int ray; float tm;
-        if (s.mode == 1) {
-            ray = r.id / s.rs.S;
-            tm = __fmul_rn(__fadd_rn(r.v[0], r.v[1]), 0.5f);
-        } else {
-            ray = r.id / s.n_imp; const int j = r.id - ray * s.n_imp;
-            const bool strat = s.jitter0 != nullptr; const float b = r.v[0];
-            const float t0 = stot_u(quantile_s(j, s.n_imp, strat, b), s.near_plane, s.far_plane);
-            const float t1 = stot_u(quantile_s(j + 1, s.n_imp, strat, b), s.near_plane, s.far_plane);
-            tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(r.v[2 + a], __fmul_rn(r.v[5 + a], tm));
-        prompt = ray / s.rays_per_cache;
-    }
-}
-
 // SDF decoder (+ analytic normal) at a list of points.  Sources and outputs as k_geo_tc (tt_tc.cuh); vscratch:
 // ws_vscratch_floats(gridDim.x, C) floats (NORMAL only).
 template <int C, bool NORMAL, bool DEFORM = false>
