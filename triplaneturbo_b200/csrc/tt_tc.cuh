@@ -581,14 +581,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tex_tc(const float* __restric
     const int64_t n_live = src.count ? (int64_t)*src.count : N;
     const int64_t n_tiles = (n_live + TC_GROUP - 1) / TC_GROUP;
 
-    for (int64_t tile = (int64_t)blockIdx.x * TC_GROUPS + group; tile < n_tiles; tile += (int64_t)gridDim.x * TC_GROUPS) {
-        const int64_t slot = tile * TC_GROUP + tg;
-        const bool valid = slot < n_live;
-        const int64_t id = valid ? (src.index ? (int64_t)src.index[slot] : slot) : 0;
+    // raw position words one tile ahead, sample id two tiles ahead (as k_tex_tc1)
+    const int64_t tstride = (int64_t)gridDim.x * TC_GROUPS, tile0 = (int64_t)blockIdx.x * TC_GROUPS + group;
+    WsRaw raw_next = ws_load_raw(src, ws_load_id(src, tile0, tg, n_live, n_tiles));
+    int id_after = ws_load_id(src, tile0 + tstride, tg, n_live, n_tiles);
+    for (int64_t tile = tile0; tile < n_tiles; tile += tstride) {
+        const WsRaw raw = raw_next;
+        raw_next = ws_load_raw(src, id_after);
+        id_after = ws_load_id(src, tile + 2 * tstride, tg, n_live, n_tiles);
+        const bool valid = raw.id >= 0;
+        const int64_t id = valid ? raw.id : 0;
         float p[3] = {0.f, 0.f, 0.f}; int prompt = 0;
         if (valid) {
             float x[3];
-            tc_point(src, id, x, prompt);
+            ws_point_from_raw(src, raw, x, prompt);
 #pragma unroll
             for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
         }

@@ -413,18 +413,40 @@ k_bwd_geo_tc(const float* __restrict__ planes, const float* __restrict__ wp, tt_
     const int64_t n_tiles = (n_live + TC_GROUP - 1) / TC_GROUP;
     bool any_tile = false;
 
-    for (int64_t tile = (int64_t)blockIdx.x * G + group; tile < n_tiles; tile += (int64_t)gridDim.x * G) {
-        const int64_t slot = tile * TC_GROUP + tg;
-        const bool valid = slot < n_live;
-        const int64_t id = valid ? (src.index ? (int64_t)src.index[slot] : slot) : 0;
-        float gs = 0.f, uu[3] = {0.f, 0.f, 0.f};
-        if (valid) { gs = gs_i[id]; uu[0] = u_i[id * 3]; uu[1] = u_i[id * 3 + 1]; uu[2] = u_i[id * 3 + 2]; }
+    // per-sample inputs one tile ahead, sample id two tiles ahead (as k_bwd_tex_tc; -DTT_BWDGEO_PREFETCH=0: loaded in place)
+#ifndef TT_BWDGEO_PREFETCH
+#define TT_BWDGEO_PREFETCH 1
+#endif
+    struct Pre { WsRaw raw; float gs, uu[3]; uint64_t m1, m2; };
+    const int64_t tstride = (int64_t)gridDim.x * G, tile0 = (int64_t)blockIdx.x * G + group;
+    auto load_pre = [&](int id) {
+        Pre q; q.raw = ws_load_raw(src, id); q.gs = q.uu[0] = q.uu[1] = q.uu[2] = 0.f; q.m1 = q.m2 = 0ull;
+        if (id >= 0) {
+            q.gs = gs_i[id]; q.uu[0] = u_i[(int64_t)id * 3]; q.uu[1] = u_i[(int64_t)id * 3 + 1]; q.uu[2] = u_i[(int64_t)id * 3 + 2];
+            q.m1 = masks[(int64_t)id * 4 + 2]; q.m2 = masks[(int64_t)id * 4 + 3];
+        }
+        return q;
+    };
+    Pre pre_next; int id_after = -1;
+    if (TT_BWDGEO_PREFETCH) {
+        pre_next = load_pre(ws_load_id(src, tile0, tg, n_live, n_tiles));
+        id_after = ws_load_id(src, tile0 + tstride, tg, n_live, n_tiles);
+    }
+    for (int64_t tile = tile0; tile < n_tiles; tile += tstride) {
+        Pre cur;
+        if (TT_BWDGEO_PREFETCH) {
+            cur = pre_next;
+            pre_next = load_pre(id_after);
+            id_after = ws_load_id(src, tile + 2 * tstride, tg, n_live, n_tiles);
+        } else cur = load_pre(ws_load_id(src, tile, tg, n_live, n_tiles));
+        const bool valid = cur.raw.id >= 0;
+        const float gs = cur.gs, uu[3] = {cur.uu[0], cur.uu[1], cur.uu[2]};
         const bool active = valid && (gs != 0.f || uu[0] != 0.f || uu[1] != 0.f || uu[2] != 0.f);
-        const uint64_t m1 = active ? masks[id * 4 + 2] : 0ull, m2 = active ? masks[id * 4 + 3] : 0ull;
+        const uint64_t m1 = active ? cur.m1 : 0ull, m2 = active ? cur.m2 : 0ull;
         int prompt = 0;
         {
             float x[3] = {0.f, 0.f, 0.f}, p[3];
-            if (active) tc_point(src, id, x, prompt);
+            if (active) ws_point_from_raw(src, cur.raw, x, prompt);
 #pragma unroll
             for (int a = 0; a < 3; ++a) p[a] = rescale1(x[a], cfg.radius);
             const float sc = 0.5f * (float)cfg.R / cfg.radius;
